@@ -1,0 +1,35 @@
+"""pytest configuration: markers, import paths, shared fixtures."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "sde-sim-rs_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun / the driver's GPU tier)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as orc
+
+    orc.build()
+    return orc
+
+
+GBM_EQ = ["dX1 = ( 0.05 * X1 ) * dt + ( 0.1 * X1) * dW1"]
+HESTON_EQ = [
+    "dS = ( 0.05 * S ) * dt + ( max(v, 0.0)^0.5 * S ) * dW1",
+    "dv = ( 2.0 * (0.04 - v) ) * dt + ( -0.21 * max(v, 0.0)^0.5 ) * dW1 + ( 0.2142428528562855 * max(v, 0.0)^0.5 ) * dW2",
+]
+
+
+def grid(D, S=None):
+    S = D if S is None else S
+    return [k / D for k in range(S + 1)]

@@ -1,0 +1,185 @@
+/* sde_b200.h — C-ABI of the B200-native SDE path-simulation engine.
+ *
+ * Drop-in boundary for the hot path of Aschii85/sde-sim-rs (crate v0.5.1).  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree).
+ * Plain pointers and sizes only; no C++/torch types.  The library (libsde_b200.so) talks to
+ * the GPU through the CUDA *driver* API (dlopen'ed libcuda.so.1 + libnvrtc.so.12), so it
+ * loads on a machine without a GPU; every compute entry point then fails with
+ * SDE_ERR_RUNTIME — there is no CPU fallback.
+ *
+ * Error model (replaces Rust Result / panics, src/py_binding.rs:20-53): every function
+ * returns 0 on success, SDE_ERR_VALUE for bad arguments / unparsable equations (the
+ * pyo3 layer's ValueError) or SDE_ERR_RUNTIME for simulation / CUDA failures (its
+ * RuntimeError).  sde_last_error() returns the thread-local message.  Nothing unwinds
+ * across this boundary.
+ */
+#ifndef SDE_B200_H
+#define SDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDE_OK 0
+#define SDE_ERR_VALUE 1
+#define SDE_ERR_RUNTIME 2
+
+/* ---- model -------------------------------------------------------------------------- */
+
+/* Opaque, immutable, shareable across threads: replaces proc::ProcessUniverse
+ * (src/proc/mod.rs:61-90). */
+typedef struct sde_universe sde_universe;
+
+/* Replaces proc::util::parse_equations(&[String], Vec<OrderedFloat<f64>>)
+ * (src/proc/util.rs:52-66).  Same grammar, same registry order (src/proc/util.rs:68-166).
+ * Deviations (documented in DESIGN.md): `times` must be finite and strictly increasing;
+ * an undefined variable is reported here instead of panicking at the first eval
+ * (src/sim/euler.rs:22). */
+int sde_universe_parse(const char* const* equations, size_t n_equations,
+                       const double* times, size_t n_times, sde_universe** out);
+void sde_universe_free(sde_universe* u);
+
+size_t sde_universe_num_processes(const sde_universe* u);           /* processes.len()            */
+size_t sde_universe_num_factors(const sde_universe* u);             /* stochastic_registry.len()  */
+size_t sde_universe_num_times(const sde_universe* u);
+const char* sde_universe_process_name(const sde_universe* u, size_t i);   /* Process::name(), mod.rs:53-58 */
+int sde_universe_process_is_levy(const sde_universe* u, size_t i);
+size_t sde_universe_process_num_terms(const sde_universe* u, size_t i);
+const char* sde_universe_factor_name(const sde_universe* u, size_t k);
+
+/* ---- options -------------------------------------------------------------------------- */
+
+enum sde_output {
+    SDE_OUT_PATHS = 0,     /* every row of every ScenarioFiltration (src/filtration.rs:16,112)     */
+    SDE_OUT_TERMINAL = 1,  /* last row only: [N][P]                                                */
+    SDE_OUT_MOMENTS = 2    /* per process (count, mean, M2) of the last row: [P][3]                */
+};
+enum sde_layout {
+    SDE_LAYOUT_NTP = 0,    /* [scenario][time][process] — the reference's row order (filtration.rs:87-113, sim/mod.rs:88-91) */
+    SDE_LAYOUT_TPN = 1     /* [time][process][scenario] — transposed, naturally coalesced          */
+};
+enum sde_scramble {
+    SDE_SCRAMBLE_CP_SHIFT_PER_PATH = 0, /* reference behaviour: u = fract(x + ChaCha8(seed+s)) (src/rng/sobol.rs:45-47,73-76) */
+    SDE_SCRAMBLE_XOR = 1,               /* one 64-bit digital-shift mask per dimension per run (what README.md:13 describes)  */
+    SDE_SCRAMBLE_NONE = 2
+};
+enum sde_icdf {
+    SDE_ICDF_REFERENCE = 0, /* A&S 26.2.23 exactly as src/proc/increment.rs:161-179, IEEE log/sqrt/div, no contraction */
+    SDE_ICDF_FAST = 1       /* same formula; table-driven log + short Newton sqrt/div in f64; |dz| <= 2e-13 vs REFERENCE */
+};
+enum sde_arith {
+    SDE_ARITH_STRICT = 0,   /* separate mul/add roundings in the reference's evaluation order       */
+    SDE_ARITH_FAST = 1      /* FMA contraction allowed (differs by <= ~1 ulp per step)              */
+};
+enum sde_rk_variant {
+    SDE_RK_REFERENCE = 0,   /* bug-compatible stale-cache semantics (src/sim/runge_kutta.rs + src/func.rs:37-39) */
+    SDE_RK_TEXTBOOK = 1     /* k1 evaluated at the settled state                                    */
+};
+
+typedef struct sde_options {
+    uint32_t struct_size;     /* = sizeof(sde_options); allows extension                            */
+    int32_t device;           /* CUDA ordinal                                                       */
+    uint64_t seed;            /* replaces rand::rng().random() (src/sim/mod.rs:28-29)               */
+    uint64_t scenario_offset; /* global index of local scenario 0 (multi-GPU shards, disjoint Sobol index ranges / RNG keys) */
+    int32_t output;           /* enum sde_output                                                    */
+    int32_t layout;           /* enum sde_layout                                                    */
+    int32_t scramble;         /* enum sde_scramble                                                  */
+    int32_t icdf;             /* enum sde_icdf                                                      */
+    int32_t arith;            /* enum sde_arith                                                     */
+    int32_t rk_variant;       /* enum sde_rk_variant                                                */
+    void* stream;             /* CUstream to launch on (NULL = library-owned stream)                */
+    const double* inject;     /* DEVICE pointer [N][S][K+1] or NULL.  Test hook for the "identical normal draws" parity check:
+                                 entry k<K is the normal z (Wiener factor) or uniform u (Poisson factor) of factor k, entry K is u[t][0] (RK's sk). */
+    int32_t tile_steps;       /* 0 = auto; time-tile length override (tuning)                       */
+    int32_t block_threads;    /* 0 = auto                                                           */
+} sde_options;
+
+void sde_options_default(sde_options* o);
+
+/* ---- simulation ----------------------------------------------------------------------- */
+
+/* A plan = one model lowered to device code for one (scheme, rng_method, options) choice,
+ * compiled for sm_100a, with its direction-number tables resident on the device.
+ * Replaces the per-call setup of sim::simulate (src/sim/mod.rs:28-39). */
+typedef struct sde_plan sde_plan;
+
+int sde_plan_create(const sde_universe* u, const char* scheme, const char* rng_method,
+                    const sde_options* opt, sde_plan** out);
+void sde_plan_free(sde_plan* p);
+/* Generated CUDA source of the plan (for inspection / offline nvcc + cuobjdump). */
+const char* sde_plan_source(const sde_plan* p);
+/* 0/1: was the cubin found in the ahead-of-time table instead of being NVRTC-compiled? */
+int sde_plan_is_prelowered(const sde_plan* p);
+/* Number of f64 elements a run over N scenarios writes for the plan's output mode. */
+size_t sde_plan_output_elems(const sde_plan* p, uint64_t n_scenarios);
+
+/* Lowering without a device (works on a CPU-only machine; used by the build check and tests):
+ * returns the generated CUDA translation unit in *source_out (free with sde_free_string) and,
+ * when `compile` is non-zero, NVRTC-compiles it for sm_100a and reports the cubin size. */
+int sde_lower_only(const sde_universe* u, const char* scheme, const char* rng_method,
+                   const sde_options* opt, int compile, char** source_out, size_t* cubin_bytes);
+void sde_free_string(char* s);
+
+/* Run N scenarios; result written to DEVICE memory `d_out` (caller-owned, e.g. a torch
+ * tensor).  Asynchronous on opt.stream.  seed / scenario_offset may differ per run.
+ * For SDE_OUT_MOMENTS d_out receives [P][3] (count, mean, M2).  kernel launches are
+ * counted in *n_launches when non-NULL. */
+int sde_plan_run_device(sde_plan* p, const char* const* init_names, const double* init_vals,
+                        size_t n_init, uint64_t n_scenarios, uint64_t seed,
+                        uint64_t scenario_offset, double* d_out, void* stream, int* n_launches);
+
+/* Same, HOST buffers: device memory is managed by the library, the result is copied to
+ * `h_out` (chunked, copy overlapped with compute).  Synchronous. */
+int sde_plan_run_host(sde_plan* p, const char* const* init_names, const double* init_vals,
+                      size_t n_init, uint64_t n_scenarios, uint64_t seed,
+                      uint64_t scenario_offset, double* h_out, int* n_launches);
+
+/* Opaque result of the one-shot call below. */
+typedef struct sde_result sde_result;
+
+/* Replaces sim::simulate(&ProcessUniverse, Vec<OrderedFloat<f64>>, HashMap<String,f64>,
+ * u64, &str, &str) -> PolarsResult<LazyFrame> (src/sim/mod.rs:20-27).  Unknown scheme ->
+ * SDE_ERR_VALUE (reference: unimplemented!() panic, src/sim/mod.rs:82); any rng_method
+ * other than "sobol" -> pseudo (src/sim/mod.rs:65).  The result stays on the device until
+ * asked for. */
+int sde_simulate(const sde_universe* u, const char* const* init_names, const double* init_vals,
+                 size_t n_init, uint64_t n_scenarios, const char* scheme, const char* rng_method,
+                 const sde_options* opt, sde_result** out);
+void sde_result_free(sde_result* r);
+void sde_result_shape(const sde_result* r, uint64_t* n_scenarios, size_t* n_times, size_t* n_processes);
+size_t sde_result_num_elems(const sde_result* r);
+const double* sde_result_values_device(const sde_result* r);
+int sde_result_values_host(const sde_result* r, double* dst, size_t n_elems);   /* the `value` column, filtration.rs:112 */
+double sde_result_kernel_ms(const sde_result* r);
+
+/* ---- building blocks exposed for parity tests and measurement ------------------------- */
+
+/* Integer Sobol points n = first .. first+count-1, all `dims` dimensions, as u64
+ * (device kernel; host output [count][dims]).  Replaces sobol::Sobol::<f64>::new(dims,
+ * JoeKuoD6::extended()) as used at src/rng/sobol.rs:15-25. */
+int sde_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out);
+/* Joe–Kuo parameters shipped with the library (for checking against an independent copy). */
+int sde_joe_kuo_params(uint32_t dims, uint32_t* poly /*[dims]*/, uint32_t* minit /*[dims][18]*/);
+/* u64 / f64 stream of ChaCha8Rng::seed_from_u64(seed) (src/rng/pseudo.rs:18,25), generated on the device. */
+int sde_chacha8_u64(int device, uint64_t seed, size_t n, uint64_t* h_out);
+/* fast_inverse_normal_cdf (src/proc/increment.rs:161-179) on the device; mode = enum sde_icdf. */
+int sde_icdf_normal(int device, int mode, const double* h_p, size_t n, double* h_out);
+/* fast_inverse_poisson_cdf (src/proc/increment.rs:182-200) on the device. */
+int sde_icdf_poisson(int device, const double* h_u, const double* h_lambda, size_t n, double* h_out);
+/* Merge per-shard (count, mean, M2) triples [n_shards][P][3] -> [P][3] (host, Chan et al.). */
+int sde_moments_merge(const double* shards, size_t n_shards, size_t n_processes, double* out);
+/* Device microbenchmarks recorded beside MEASURED_PEAKS.json: pure-write GB/s, DFMA / FFMA TFLOP/s. */
+int sde_measure_peaks(int device, double* fill_gbs, double* dfma_tflops, double* ffma_tflops);
+
+const char* sde_last_error(void);
+const char* sde_version(void);
+/* 1 when libcuda + a device are usable from this process. */
+int sde_cuda_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDE_B200_H */

@@ -1,0 +1,207 @@
+// cuda_rt.cpp — see cuda_rt.h.
+#include "cuda_rt.h"
+
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#define SDE_STR2(x) #x
+#define SDE_STR(x) SDE_STR2(x)
+
+extern "C" {
+extern const char sde_blob_sim_kernel_cuh_begin[], sde_blob_sim_kernel_cuh_end[];
+extern const char sde_blob_device_rng_cuh_begin[], sde_blob_device_rng_cuh_end[];
+extern const char sde_blob_device_icdf_cuh_begin[], sde_blob_device_icdf_cuh_end[];
+extern const char sde_blob_icdf_tables_cuh_begin[], sde_blob_icdf_tables_cuh_end[];
+extern const char sde_blob_expr_helpers_cuh_begin[], sde_blob_expr_helpers_cuh_end[];
+}
+
+namespace sde {
+namespace {
+
+void* open_first(const char* const* names, std::string* tried) {
+    for (int i = 0; names[i]; ++i) {
+        if (void* h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL)) return h;
+        if (tried) { *tried += names[i]; *tried += " "; }
+    }
+    return nullptr;
+}
+
+struct DriverState {
+    DriverApi api{};
+    bool ok = false;
+    std::string why;
+};
+
+DriverState& driver_state() {
+    static DriverState st;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libcuda.so.1", "libcuda.so", nullptr};
+        std::string tried;
+        void* h = open_first(names, &tried);
+        if (!h) { st.why = "CUDA driver library not found (tried " + tried + "): no GPU, and this library has no CPU fallback"; return; }
+        bool missing = false;
+        std::string miss;
+#define SDE_LOAD(field)                                                                 \
+        st.api.field = reinterpret_cast<decltype(st.api.field)>(dlsym(h, SDE_STR(field))); \
+        if (!st.api.field) { missing = true; miss += SDE_STR(field) " "; }
+        SDE_LOAD(cuInit) SDE_LOAD(cuDeviceGet) SDE_LOAD(cuDeviceGetCount) SDE_LOAD(cuDeviceGetAttribute)
+        SDE_LOAD(cuDevicePrimaryCtxRetain) SDE_LOAD(cuCtxSetCurrent) SDE_LOAD(cuCtxGetCurrent)
+        SDE_LOAD(cuModuleLoadData) SDE_LOAD(cuModuleUnload) SDE_LOAD(cuModuleGetFunction)
+        SDE_LOAD(cuFuncSetAttribute) SDE_LOAD(cuFuncGetAttribute) SDE_LOAD(cuLaunchKernel)
+        SDE_LOAD(cuMemAlloc) SDE_LOAD(cuMemFree) SDE_LOAD(cuMemcpyHtoD) SDE_LOAD(cuMemcpyDtoH)
+        SDE_LOAD(cuMemcpyHtoDAsync) SDE_LOAD(cuMemcpyDtoHAsync) SDE_LOAD(cuMemsetD8Async)
+        SDE_LOAD(cuMemHostAlloc) SDE_LOAD(cuMemFreeHost) SDE_LOAD(cuMemHostRegister) SDE_LOAD(cuMemHostUnregister)
+        SDE_LOAD(cuMemGetInfo) SDE_LOAD(cuStreamCreate) SDE_LOAD(cuStreamDestroy) SDE_LOAD(cuStreamSynchronize)
+        SDE_LOAD(cuStreamWaitEvent) SDE_LOAD(cuEventCreate) SDE_LOAD(cuEventDestroy) SDE_LOAD(cuEventRecord)
+        SDE_LOAD(cuEventSynchronize) SDE_LOAD(cuEventElapsedTime) SDE_LOAD(cuGetErrorString)
+        SDE_LOAD(cuOccupancyMaxActiveBlocksPerMultiprocessor)
+#undef SDE_LOAD
+        if (missing) { st.why = "CUDA driver is missing symbols: " + miss; return; }
+        CUresult r = st.api.cuInit(0);
+        if (r != CUDA_SUCCESS) { st.why = "cuInit failed (" + std::to_string((int)r) + "): no usable GPU"; return; }
+        int n = 0;
+        if (st.api.cuDeviceGetCount(&n) != CUDA_SUCCESS || n <= 0) { st.why = "no CUDA device visible"; return; }
+        st.ok = true;
+    });
+    return st;
+}
+
+struct NvrtcState {
+    NvrtcApi api{};
+    bool ok = false;
+    std::string why;
+};
+
+NvrtcState& nvrtc_state() {
+    static NvrtcState st;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", nullptr};
+        std::string tried;
+        void* h = open_first(names, &tried);
+        if (!h) { st.why = "NVRTC not found (tried " + tried + ")"; return; }
+        bool missing = false;
+#define SDE_LOAD(field)                                                                 \
+        st.api.field = reinterpret_cast<decltype(st.api.field)>(dlsym(h, SDE_STR(field))); \
+        if (!st.api.field) missing = true;
+        SDE_LOAD(nvrtcCreateProgram) SDE_LOAD(nvrtcDestroyProgram) SDE_LOAD(nvrtcCompileProgram)
+        SDE_LOAD(nvrtcGetCUBINSize) SDE_LOAD(nvrtcGetCUBIN) SDE_LOAD(nvrtcGetProgramLogSize)
+        SDE_LOAD(nvrtcGetProgramLog) SDE_LOAD(nvrtcGetErrorString)
+#undef SDE_LOAD
+        if (missing) { st.why = "NVRTC is missing symbols"; return; }
+        st.ok = true;
+    });
+    return st;
+}
+
+}  // namespace
+
+const DriverApi& driver() {
+    DriverState& st = driver_state();
+    if (!st.ok) throw CudaError{st.why};
+    return st.api;
+}
+
+bool driver_available(std::string* why) {
+    DriverState& st = driver_state();
+    if (!st.ok && why) *why = st.why;
+    return st.ok;
+}
+
+const NvrtcApi& nvrtc() {
+    NvrtcState& st = nvrtc_state();
+    if (!st.ok) throw CudaError{st.why};
+    return st.api;
+}
+
+void cu_check(CUresult r, const char* what) {
+    if (r == CUDA_SUCCESS) return;
+    const char* s = nullptr;
+    DriverState& st = driver_state();
+    if (st.api.cuGetErrorString) st.api.cuGetErrorString(r, &s);
+    throw CudaError{std::string(what) + ": " + (s ? s : "unknown CUDA error") + " (" + std::to_string((int)r) + ")"};
+}
+
+void use_device(int device) {
+    const DriverApi& d = driver();
+    static std::mutex mu;
+    static CUcontext ctxs[64] = {};
+    if (device < 0 || device >= 64) throw CudaError{"bad device ordinal"};
+    CUcontext ctx;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!ctxs[device]) {
+            CUdevice dev;
+            cu_check(d.cuDeviceGet(&dev, device), "cuDeviceGet");
+            cu_check(d.cuDevicePrimaryCtxRetain(&ctxs[device], dev), "cuDevicePrimaryCtxRetain");
+        }
+        ctx = ctxs[device];
+    }
+    cu_check(d.cuCtxSetCurrent(ctx), "cuCtxSetCurrent");
+}
+
+int sm_count(int device) {
+    const DriverApi& d = driver();
+    CUdevice dev;
+    cu_check(d.cuDeviceGet(&dev, device), "cuDeviceGet");
+    int n = 0;
+    cu_check(d.cuDeviceGetAttribute(&n, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev), "cuDeviceGetAttribute");
+    return n;
+}
+
+std::vector<char> nvrtc_compile(const std::string& source, const std::string& name, std::string* log) {
+    const NvrtcApi& n = nvrtc();
+    struct H { const char* name; const char* b; const char* e; };
+    const H hs[] = {
+        {"sde_sim_kernel.cuh", sde_blob_sim_kernel_cuh_begin, sde_blob_sim_kernel_cuh_end},
+        {"sde_device_rng.cuh", sde_blob_device_rng_cuh_begin, sde_blob_device_rng_cuh_end},
+        {"sde_device_icdf.cuh", sde_blob_device_icdf_cuh_begin, sde_blob_device_icdf_cuh_end},
+        {"sde_icdf_tables.cuh", sde_blob_icdf_tables_cuh_begin, sde_blob_icdf_tables_cuh_end},
+        {"sde_expr_helpers.cuh", sde_blob_expr_helpers_cuh_begin, sde_blob_expr_helpers_cuh_end},
+    };
+    std::vector<std::string> bodies;
+    std::vector<const char*> names, ptrs;
+    for (const H& h : hs) bodies.emplace_back(h.b, h.e);
+    for (size_t i = 0; i < bodies.size(); ++i) { names.push_back(hs[i].name); ptrs.push_back(bodies[i].c_str()); }
+    nvrtcProgram prog;
+    nvrtcResult r = n.nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), (int)names.size(), ptrs.data(), names.data());
+    if (r != NVRTC_SUCCESS) throw CudaError{std::string("nvrtcCreateProgram: ") + n.nvrtcGetErrorString(r)};
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
+    r = n.nvrtcCompileProgram(prog, 3, opts);
+    size_t ls = 0;
+    n.nvrtcGetProgramLogSize(prog, &ls);
+    std::string lg(ls, '\0');
+    if (ls) n.nvrtcGetProgramLog(prog, lg.data());
+    if (log) *log = lg;
+    if (r != NVRTC_SUCCESS) {
+        n.nvrtcDestroyProgram(&prog);
+        throw CudaError{std::string("NVRTC compilation failed: ") + n.nvrtcGetErrorString(r) + "\n" + lg};
+    }
+    size_t cs = 0;
+    n.nvrtcGetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    n.nvrtcGetCUBIN(prog, cubin.data());
+    n.nvrtcDestroyProgram(&prog);
+    if (cs == 0) throw CudaError{"NVRTC produced an empty cubin"};
+    return cubin;
+}
+
+void DeviceBuffer::alloc(size_t bytes) {
+    release();
+    if (bytes == 0) return;
+    cu_check(driver().cuMemAlloc(&ptr_, bytes), "cuMemAlloc");
+    bytes_ = bytes;
+}
+void DeviceBuffer::release() {
+    if (ptr_) { driver_state().api.cuMemFree(ptr_); ptr_ = 0; bytes_ = 0; }
+}
+void DeviceBuffer::upload(const void* src, size_t bytes) {
+    if (bytes > bytes_) alloc(bytes);
+    if (bytes) cu_check(driver().cuMemcpyHtoD(ptr_, src, bytes), "cuMemcpyHtoD");
+}
+
+}  // namespace sde

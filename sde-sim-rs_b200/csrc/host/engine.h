@@ -1,0 +1,78 @@
+// engine.h — plans and launches: the host side of sim::simulate (src/sim/mod.rs:20-92).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cuda_rt.h"
+#include "lower.h"
+#include "universe.h"
+
+namespace sde {
+
+// ---- Joe–Kuo / Sobol host tables (replaces sobol::params::JoeKuoD6::extended, src/rng/sobol.rs:7,16)
+constexpr uint32_t kMaxSobolDims = 21201;
+void joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit /*[dims][18]*/);
+// V[d][b], b < 32: top 32 bits of the 64-bit direction numbers.  lane[d][l] = x_d(l), l < 32.
+void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane);
+// u64 #i of ChaCha8Rng::seed_from_u64(seed) (host copy, used for the XOR digital-shift masks)
+void chacha8_u64_host(uint64_t seed, size_t n, uint64_t* out);
+
+struct PlanOptions {
+    int device = 0;
+    LowerOptions lower;
+};
+
+class Plan {
+  public:
+    Plan(const Universe& u, const PlanOptions& opt);
+    ~Plan();
+    Plan(const Plan&) = delete;
+    Plan& operator=(const Plan&) = delete;
+
+    const Universe& universe() const { return u_; }
+    const Lowered& lowered() const { return low_; }
+    const PlanOptions& options() const { return opt_; }
+    bool prelowered() const { return prelowered_; }
+    size_t output_elems(uint64_t n) const;
+
+    // Asynchronous on `stream` (nullptr = the plan's own stream, then synchronised before return).
+    void run_device(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
+                    uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches);
+    void run_host(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
+                  uint64_t scenario_offset, double* h_out, int* n_launches);
+    double last_kernel_ms() const { return last_ms_; }
+    int device() const { return opt_.device; }
+
+  private:
+    Universe u_;
+    PlanOptions opt_;
+    Lowered low_;
+    bool prelowered_ = false;
+    CUmodule mod_ = nullptr;
+    CUfunction fn_sim_ = nullptr, fn_fin_ = nullptr;
+    DeviceBuffer d_times_, d_dts_, d_sqrt_dts_, d_x0_, d_V_, d_lane_, d_masks_, d_partials_;
+    std::vector<double> x0_host_;
+    bool masks_valid_ = false;
+    uint64_t masks_seed_ = 0;
+    CUstream own_stream_ = nullptr, copy_stream_ = nullptr;
+    CUevent ev_a_ = nullptr, ev_b_ = nullptr;
+    DeviceBuffer d_chunk_[2];
+    CUevent ev_done_[2] = {nullptr, nullptr}, ev_copied_[2] = {nullptr, nullptr};
+    double last_ms_ = 0.0;
+
+    void set_initial_values(const std::vector<std::pair<std::string, double>>& init, CUstream stream);
+    void ensure_masks(uint64_t seed, CUstream stream);
+    void launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches);
+};
+
+// ---- stand-alone building blocks (ahead-of-time cubin)
+void util_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out);
+void util_chacha8_u64(int device, uint64_t seed, size_t n, uint64_t* h_out);
+void util_icdf_normal(int device, int mode, const double* h_p, size_t n, double* h_out);
+void util_icdf_poisson(int device, const double* h_u, const double* h_lambda, size_t n, double* h_out);
+void util_measure_peaks(int device, double* fill_gbs, double* dfma_tflops, double* ffma_tflops);
+void moments_merge(const double* shards, size_t n_shards, size_t P, double* out);
+
+}  // namespace sde

@@ -1,0 +1,239 @@
+// lower.cpp — model IR -> CUDA C++ (see lower.h).
+#include "lower.h"
+
+#include <algorithm>
+#include <numeric>
+#include <sstream>
+
+namespace sde {
+namespace {
+
+// Where the reference's ScenarioFiltrationCache points while a step is being generated.
+// The cache is refreshed from the raw rows only when an expression is evaluated at a time
+// different from cache.time (src/func.rs:37-39, src/filtration.rs:70-79); writes to the
+// rows never touch it (filtration.rs:61-64).  Times are strictly increasing, so within the
+// step for index t there are exactly three possibilities.
+enum CacheAt { OLD, CUR, NEXT };
+
+class StepGen {
+  public:
+    StepGen(const Universe& u, const LowerOptions& opt) : u_(u), opt_(opt) {}
+
+    // Emits the body of sde_model_step given the cache position on entry; returns it on exit.
+    CacheAt generate(CacheAt enter, std::ostringstream& o) {
+        state_ = enter;
+        o_ = &o;
+        const int P = u_.P();
+        for (int p = 0; p < P; ++p) line("double n" + std::to_string(p) + " = 0.0;");   // row t+1 is zero until set (filtration.rs:28)
+        if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
+        for (int p = 0; p < P; ++p) line("row[" + std::to_string(p) + "] = n" + std::to_string(p) + ";");
+        return state_;
+    }
+
+  private:
+    const Universe& u_;
+    const LowerOptions& opt_;
+    CacheAt state_ = OLD;
+    std::ostringstream* o_ = nullptr;
+
+    void line(const std::string& s) { *o_ << "    " << s << "\n"; }
+    std::string mul(const std::string& a, const std::string& b) const { return opt_.strict ? "__dmul_rn(" + a + ", " + b + ")" : "(" + a + " * " + b + ")"; }
+    std::string add(const std::string& a, const std::string& b) const { return opt_.strict ? "__dadd_rn(" + a + ", " + b + ")" : "(" + a + " + " + b + ")"; }
+
+    // ScenarioFiltration::refresh_cache (filtration.rs:70-79): reload every registered name from the row of `at`.
+    void refresh(CacheAt at) {
+        line(at == CUR ? "// cache refresh from row t (func.rs:37-39)" : "// cache refresh from row t+1 as written so far (func.rs:37-39)");
+        std::vector<int> idx;
+        for (auto& kv : u_.process_registry) idx.push_back(kv.second);
+        std::sort(idx.begin(), idx.end());
+        for (int i : idx) {
+            std::string s = std::to_string(i);
+            line("c[" + s + "] = " + (at == CUR ? "row[" + s + "]" : "n" + s) + ";");
+        }
+        line(std::string("ct = ") + (at == CUR ? "t_cur;" : "t_next;"));
+        state_ = at;
+    }
+    // Function::eval (func.rs:32-42)
+    std::string eval(const Expr& e, CacheAt at) {
+        if (state_ != at) refresh(at);
+        return e.emit_cuda(opt_.strict);
+    }
+    // Incrementor::sample (increment.rs:46-59, 89-97, 137-148)
+    std::string increment(const Term& t) {
+        if (t.kind == IncKind::Time) return "dt";
+        std::string z = "zu[" + std::to_string(t.factor) + "]";
+        if (t.kind == IncKind::Wiener) return mul("sqrt_dt", z);
+        std::string lam = eval(t.lambda, CUR);               // lambda.eval(ts[time_idx], ..) * dt
+        return "sde_icdf_poisson(" + z + ", " + mul(lam, "dt") + ")";
+    }
+
+    void euler() {                                           // src/sim/euler.rs:5-37
+        for (int p : u_.levy_indices) {
+            const Process& pr = u_.processes[p];
+            std::string sp = std::to_string(p);
+            line("{   // Levy process " + sp + " '" + pr.name + "' (euler.rs:15-28)");
+            line("double val = row[" + sp + "];");
+            for (const Term& t : pr.terms) {
+                std::string cf = eval(t.coeff, CUR);
+                line("{ const double cf = " + cf + ";");
+                std::string x = increment(t);
+                line("  const double x = " + x + ";");
+                line("  val = " + add("val", mul("cf", "x")) + "; }");
+            }
+            line("n" + sp + " = val; }");
+        }
+        for (int a : u_.algebraic_indices) {                 // euler.rs:31-36
+            std::string ex = eval(u_.processes[a].algebraic, NEXT);
+            line("n" + std::to_string(a) + " = " + ex + ";   // algebraic '" + u_.processes[a].name + "'");
+        }
+    }
+
+    void runge_kutta() {                                     // src/sim/runge_kutta.rs:5-107
+        const int P = u_.P();
+        line("const double sk = (u0 > 0.5) ? 1.0 : -1.0;   // runge_kutta.rs:18-22");
+        if (opt_.rk_textbook) state_ = OLD;                  // textbook variant: k1 at the settled row
+        for (int p = 0; p < P; ++p) {                        // :26-35 pre-sample, reused by k1 and k2
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            for (size_t j = 0; j < pr.terms.size(); ++j) {
+                std::string x = increment(pr.terms[j]);
+                line("const double inc_" + std::to_string(p) + "_" + std::to_string(j) + " = " + x + ";");
+            }
+        }
+        for (int p = 0; p < P; ++p) line("const double x" + std::to_string(p) + " = row[" + std::to_string(p) + "];");   // :38-42
+        for (int p = 0; p < P; ++p) {                        // :45-55  k1
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            std::string k = "k1_" + std::to_string(p);
+            line("double " + k + " = 0.0;");
+            for (size_t j = 0; j < pr.terms.size(); ++j) {
+                std::string cf = eval(pr.terms[j].coeff, CUR);
+                line(k + " = " + add(k, mul(cf, "inc_" + std::to_string(p) + "_" + std::to_string(j))) + ";");
+            }
+        }
+        for (int p = 0; p < P; ++p) {                        // :62-78  probe row
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            std::string sp = std::to_string(p);
+            line("{ double pert = 0.0;");
+            for (const Term& t : pr.terms) {
+                if (t.kind != IncKind::Wiener) continue;
+                std::string cf = eval(t.coeff, CUR);
+                line("  pert = " + add("pert", mul(mul(cf, "sk"), "sqrt_dt")) + ";");
+            }
+            line("  n" + sp + " = " + add(add("x" + sp, "k1_" + sp), "pert") + "; }");
+        }
+        for (int p = 0; p < P; ++p) {                        // :81-91  k2 at the probe row
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            std::string k = "k2_" + std::to_string(p);
+            line("double " + k + " = 0.0;");
+            for (size_t j = 0; j < pr.terms.size(); ++j) {
+                std::string cf = eval(pr.terms[j].coeff, NEXT);
+                line(k + " = " + add(k, mul(cf, "inc_" + std::to_string(p) + "_" + std::to_string(j))) + ";");
+            }
+        }
+        for (int p : u_.levy_indices) {                      // :94-97
+            std::string sp = std::to_string(p);
+            line("n" + sp + " = " + add("x" + sp, mul("0.5", add("k1_" + sp, "k2_" + sp))) + ";");
+        }
+        if (opt_.rk_textbook && !u_.algebraic_indices.empty()) state_ = OLD;
+        for (int a : u_.algebraic_indices) {                 // :101-106 (sees the probe row: cache not refreshed)
+            std::string ex = eval(u_.processes[a].algebraic, NEXT);
+            line("n" + std::to_string(a) + " = " + ex + ";   // algebraic '" + u_.processes[a].name + "'");
+        }
+    }
+};
+
+int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
+
+}  // namespace
+
+Lowered lower_model(const Universe& u, const LowerOptions& opt) {
+    const int P = u.P(), K = u.K();
+    if (P == 0) throw ExprError{"no equations"};
+    if (u.T() < 2) throw ExprError{"time_steps needs at least two points"};
+    if (opt.scheme == SCHEME_RK && K == 0)
+        throw ExprError{"runge-kutta needs at least one stochastic factor (the reference panics: rng index 0 out of bounds, src/rng/pseudo.rs:53-58)"};
+    Lowered L;
+    const bool chacha = opt.rng == RNG_PSEUDO || opt.rng == RNG_SOBOL_CP;
+    const bool sobol = opt.rng == RNG_SOBOL_CP || opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW;
+    const int KK = K > 0 ? K : 1;
+    L.ch = (chacha && K > 0) ? 8 / gcd_int(8, K) : 1;
+
+    // ---- steady-state cache position: where does one step leave the cache?
+    {
+        std::ostringstream scratch;
+        StepGen probe(u, opt);
+        CacheAt exit_state = probe.generate(OLD, scratch);
+        L.enter_eq = (exit_state == NEXT);                   // this step's t+1 is the next step's t
+    }
+    std::ostringstream body;
+    StepGen gen(u, opt);
+    gen.generate(L.enter_eq ? CUR : OLD, body);
+
+    // ---- launch shape
+    L.block = opt.block > 0 ? opt.block : 256;
+    int tt = opt.tile_steps;
+    if (tt <= 0) {
+        tt = 32;
+        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 32 / P);
+        if (sobol) tt = std::min(tt, std::max(1, 512 / KK));
+    }
+    tt = std::max(L.ch, (tt / L.ch) * L.ch);
+    L.tt = tt;
+    auto smem_for = [&](int block) {
+        const int nw = block / 32;
+        size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)128 * 2 * 8 * 8 : 0;
+        size_t tile = (opt.out == OUT_PATHS_NTP) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
+        size_t bw = sobol ? (size_t)tt * KK * nw * 4 : 0;
+        size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
+        return icdf + tile + bw + mom;
+    };
+    if (opt.block <= 0) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
+    L.smem_bytes = smem_for(L.block);
+    if (L.smem_bytes > 227 * 1024) throw ExprError{"model too large for the shared-memory staging tile (P = " + std::to_string(P) + ")"};
+    {
+        const int regs_est = std::min(255, 56 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
+        int by_regs = std::max(1, 65536 / (L.block * regs_est));
+        int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / std::max<size_t>(L.smem_bytes, 1024));
+        int by_threads = std::max(1, 2048 / L.block);
+        L.min_blocks = std::max(1, std::min({by_regs, by_smem, by_threads}));
+    }
+
+    // ---- translation unit
+    std::ostringstream s;
+    s << "// Generated by libsde_b200 (csrc/host/lower.cpp) — model lowered from equation strings.\n";
+    for (int p = 0; p < P; ++p) {
+        const Process& pr = u.processes[p];
+        s << "//   process " << p << " '" << pr.name << "' " << (pr.levy ? "levy" : "algebraic");
+        if (pr.levy) for (const Term& t : pr.terms) s << " | (" << t.coeff.source() << ") * " << (t.kind == IncKind::Time ? "dt" : u.factor_names[t.factor]);
+        else s << " = " << pr.algebraic.source();
+        s << "\n";
+    }
+    s << "#define SDE_P " << P << "\n#define SDE_K " << K << "\n#define SDE_KK " << KK << "\n";
+    s << "#define SDE_SCHEME " << opt.scheme << "\n#define SDE_RNG " << opt.rng << "\n#define SDE_OUT " << opt.out << "\n";
+    s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
+    s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
+    s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
+    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n";
+    s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
+    s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
+    {
+        bool any = false;
+        for (int k = 0; k < K; ++k) if (u.factor_is_wiener[k]) { s << (any ? " || " : "") << "k == " << k; any = true; }
+        if (!any) s << "false";
+    }
+    s << "; }\n";
+    s << "// one step of " << (opt.scheme == SCHEME_EULER ? "euler_iteration (src/sim/euler.rs:5-37)" : "runge_kutta_iteration (src/sim/runge_kutta.rs:5-107)")
+      << "; cache enters " << (L.enter_eq ? "AT times[t] (stale values, not refreshed)" : "behind times[t] (refreshed at the first evaluation)") << "\n";
+    s << "__device__ __forceinline__ void sde_model_step(double (&row)[SDE_P], double (&c)[SDE_P], double& ct, const double (&zu)[SDE_KK],\n"
+         "                                               const double u0, const double t_cur, const double t_next, const double dt, const double sqrt_dt) {\n";
+    s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
+    s << body.str();
+    s << "}\n#include \"sde_sim_kernel.cuh\"\n";
+    L.source = s.str();
+    return L;
+}
+
+}  // namespace sde

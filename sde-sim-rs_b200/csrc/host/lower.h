@@ -1,0 +1,41 @@
+// lower.h — lowering of a parsed model to the CUDA translation unit of one plan.
+//
+// Replaces the interpretive inner loops of euler_iteration (src/sim/euler.rs:5-37) and
+// runge_kutta_iteration (src/sim/runge_kutta.rs:5-107): the per-step control flow, the
+// term order and the reference's time-keyed cache rule (src/func.rs:37-39) are resolved
+// here, at lowering time, into straight-line device code over registers.
+#pragma once
+#include <string>
+
+#include "universe.h"
+
+namespace sde {
+
+enum RngMode { RNG_PSEUDO = 0, RNG_SOBOL_CP = 1, RNG_SOBOL_XOR = 2, RNG_SOBOL_RAW = 3, RNG_INJECT = 4 };
+enum OutMode { OUT_PATHS_NTP = 0, OUT_PATHS_TPN = 1, OUT_TERMINAL = 2, OUT_MOMENTS = 3 };
+enum SchemeId { SCHEME_EULER = 0, SCHEME_RK = 1 };
+
+struct LowerOptions {
+    int scheme = SCHEME_EULER;
+    int rng = RNG_PSEUDO;
+    int out = OUT_PATHS_NTP;
+    int icdf = 0;            // 0 reference, 1 fast
+    bool strict = true;      // no FMA contraction in model arithmetic
+    bool rk_textbook = false;
+    int block = 0;           // 0 = auto
+    int tile_steps = 0;      // 0 = auto
+};
+
+struct Lowered {
+    std::string source;      // complete translation unit (includes sde_sim_kernel.cuh)
+    int block = 256;
+    int min_blocks = 1;
+    int tt = 32;
+    int ch = 1;
+    size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
+    bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)
+};
+
+Lowered lower_model(const Universe& u, const LowerOptions& opt);
+
+}  // namespace sde

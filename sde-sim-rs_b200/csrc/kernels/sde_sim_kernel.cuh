@@ -1,0 +1,297 @@
+// sde_sim_kernel.cuh — the fused path-simulation kernel (sm_100a).
+//
+// One launch replaces the whole of sim::simulate's parallel region (src/sim/mod.rs:41-88):
+// per-scenario RNG construction (src/rng/pseudo.rs:14-20, src/rng/sobol.rs:35-53), the time
+// loop (src/sim/mod.rs:68-84) calling euler_iteration / runge_kutta_iteration, the
+// Wiener/Poisson incrementors (src/proc/increment.rs:89-148) and the dense Filtration rows
+// (src/filtration.rs:55-64,112).  One thread owns one path; its state row and the
+// expression cache live in registers; the model's drift/diffusion expressions arrive as
+// generated device code (`sde_model_step`, emitted by csrc/host/lower.cpp from the parsed
+// equations) in the translation unit that includes this header.
+//
+// Macros expected from the generated prelude:
+//   SDE_P, SDE_K                   processes / stochastic factors
+//   SDE_RNG                        0 pseudo(ChaCha8)  1 sobol+per-path CP shift (reference)
+//                                  2 sobol+XOR digital shift  3 sobol raw  4 injected draws
+//   SDE_OUT                        0 paths [N][T][P]  1 paths [T][P][N]  2 terminal [N][P]  3 moments
+//   SDE_ICDF                       0 reference  1 fast
+//   SDE_NEEDS_U0                   1 when the scheme consumes u[t][0] directly (Runge–Kutta sk)
+//   SDE_BLOCK, SDE_MIN_BLOCKS      launch bounds
+//   SDE_TT                         time-tile length (multiple of SDE_CH)
+//   SDE_CH                         ChaCha chunk: 8 / gcd(8, K) steps consume whole blocks
+//   sde_factor_is_wiener(k)        constexpr predicate
+//   sde_model_step(row, cache, ct, zu, u0, t_cur, t_next, dt, sqrt_dt)
+#pragma once
+#include "sde_device_rng.cuh"
+#include "sde_device_icdf.cuh"
+
+struct SdeParams {
+    sde_u64 n_paths;       // local scenario count N
+    sde_u64 scen_offset;   // global index of local scenario 0
+    sde_u64 n_base;        // point index of thread 0 of CTA 0 (multiple of SDE_BLOCK)
+    sde_u64 seed;
+    int n_steps;           // S = T - 1
+    int reserved;
+    const double* times;      // [T]
+    const double* dts;        // [S]   times[t+1] - times[t]            (increment.rs:38-41)
+    const double* sqrt_dts;   // [S]   sqrt(dts[t])                     (increment.rs:75-79)
+    const double* x0;         // [P]   row 0                            (filtration.rs:42-50)
+    const sde_u32* sobol_V;     // [S*K][32] direction numbers, top 32 bits
+    const sde_u32* sobol_lane;  // [S*K][32] x_d(lane)
+    const sde_u64* xor_masks;   // [S*K]
+    const double* inject;     // [N][S][K+1]
+    double* out;
+    double* partials;         // moments: [grid][P][3]
+};
+
+#define SDE_NW (SDE_BLOCK / 32)
+#define SDE_USES_CHACHA (SDE_RNG == 0 || SDE_RNG == 1)
+#define SDE_USES_SOBOL (SDE_RNG == 1 || SDE_RNG == 2 || SDE_RNG == 3)
+#ifndef SDE_KK
+#define SDE_KK (SDE_K > 0 ? SDE_K : 1)
+#endif
+// leading dimension of a warp's staging row: odd => conflict-free column writes
+#define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
+
+// shared-memory carve-up (bytes); mirrored by the host in engine.cpp via the same macros
+#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
+#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
+#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * SDE_NW * 4) : 0)
+#define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_MOM_BYTES)
+
+struct SdeMoments { double n, mean, m2; };
+
+// Chan et al. pairwise merge of (count, mean, M2).
+__device__ __forceinline__ SdeMoments sde_mom_merge(const SdeMoments a, const SdeMoments b) {
+    SdeMoments r;
+    r.n = a.n + b.n;
+    if (r.n == 0.0) { r.mean = 0.0; r.m2 = 0.0; return r; }
+    const double d = b.mean - a.mean;
+    const double f = b.n / r.n;
+    r.mean = a.mean + d * f;
+    r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+    return r;
+}
+
+__device__ __forceinline__ double sde_uniform_to_draw(double u, bool wiener, const double* s_icdf, int lane) {
+    if (!wiener) return u;                               // Poisson factors consume the uniform itself
+#if SDE_ICDF == 1
+    return sde_icdf_normal_fast(u, s_icdf, lane);
+#else
+    return sde_icdf_normal_reference(u);
+#endif
+}
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
+    extern __shared__ double4 sde_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
+    double* s_icdf = reinterpret_cast<double*>(smem);
+    double* s_tile = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES);
+    sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES);
+    double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_BW_BYTES);
+    (void)s_icdf; (void)s_tile; (void)s_bw; (void)s_mom;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int S = prm.n_steps;
+    const int T = S + 1;
+
+    // thread -> point index n -> scenario (n - 5): the reference skips 5 points (sobol.rs:17)
+    const sde_u64 n_cta = prm.n_base + (sde_u64)blockIdx.x * SDE_BLOCK;
+    const sde_u64 n = n_cta + (sde_u64)tid;
+    const sde_u64 first_n = prm.scen_offset + 5ull;
+    const bool valid = (n >= first_n) && (n - first_n < prm.n_paths);
+    const long long s_local = (long long)(n - first_n);           // may be "negative" for the <=5 leading pad threads
+    const sde_u64 s_global = n - 5ull;
+
+#if SDE_ICDF == 1 && SDE_RNG != 4
+    sde_icdf_table_load(s_icdf, tid, SDE_BLOCK);
+    __syncthreads();
+#endif
+
+    // ScenarioFiltration::new — row 0 from initial_values, cache loaded from row 0 (filtration.rs:42-51)
+    double row[SDE_P], cache[SDE_P];
+    double ct = __ldg(prm.times);
+#pragma unroll
+    for (int p = 0; p < SDE_P; ++p) { row[p] = __ldg(prm.x0 + p); cache[p] = row[p]; }
+
+#if SDE_USES_CHACHA
+    SdeChaCha8Stream cha;
+    cha.init(prm.seed + s_global);                                 // sim/mod.rs:56,65 (wrapping add)
+#endif
+
+#if SDE_OUT == 0
+    if (valid) {
+#pragma unroll
+        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)s_local * T * SDE_P + p] = row[p];
+    }
+    double* my_tile = s_tile + (size_t)(warp * 32 + lane) * SDE_TILE_LD;
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+    const long long s_warp0 = s_local - lane;
+#elif SDE_OUT == 1
+    if (valid) {
+#pragma unroll
+        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)p * prm.n_paths + s_local] = row[p];
+    }
+#endif
+
+    for (int t0 = 0; t0 < S; t0 += SDE_TT) {
+        const int t_end = min(t0 + SDE_TT, S);
+#if SDE_USES_SOBOL
+        // fold the CTA/warp part of the point index into shared memory for this tile's dimensions
+        __syncthreads();
+        {
+            const int nd = (t_end - t0) * SDE_K;
+            for (int e = tid; e < nd * SDE_NW; e += SDE_BLOCK) {
+                const int dl = e / SDE_NW, w = e - dl * SDE_NW;
+                const size_t d = (size_t)t0 * SDE_K + dl;
+                s_bw[e] = sde_sobol_point32(prm.sobol_V + d * 32, (sde_u32)n_cta + 32u * (sde_u32)w);
+            }
+        }
+        __syncthreads();
+#endif
+        for (int tc = t0; tc < t_end; tc += SDE_CH) {
+#pragma unroll
+            for (int j = 0; j < SDE_CH; ++j) {
+                const int t = tc + j;
+                if (t < t_end) {
+                    double zu[SDE_KK];
+                    double u0 = 0.0;
+                    zu[0] = 0.0;
+#if SDE_RNG == 4
+                    {
+                        const double* src = prm.inject + ((size_t)(valid ? s_local : 0) * S + t) * (SDE_K + 1);
+#pragma unroll
+                        for (int k = 0; k < SDE_K; ++k) zu[k] = __ldg(src + k);
+                        u0 = __ldg(src + SDE_K);
+                    }
+#else
+#pragma unroll
+                    for (int k = 0; k < SDE_K; ++k) {
+                        double u;
+#if SDE_USES_CHACHA
+                        const int slot = (j * SDE_K + k) & 7;      // compile-time after unrolling
+                        if (slot == 0) cha.refill();
+                        const double uc = (double)(long long)cha.bits53(slot) * 1.1102230246251565e-16;   // * 2^-53
+#endif
+#if SDE_USES_SOBOL
+                        const size_t d = (size_t)t * SDE_K + k;
+                        const sde_u32 x = s_bw[((t - t0) * SDE_K + k) * SDE_NW + warp] ^ __ldg(prm.sobol_lane + d * 32 + lane);
+#endif
+#if SDE_RNG == 0
+                        u = uc;
+#elif SDE_RNG == 1
+                        {   // RandomShiftScrambler::scramble: (raw + shift).fract()   (sobol.rs:73-76)
+                            const double v = (double)x * 2.3283064365386963e-10 + uc;
+                            u = (v >= 1.0) ? v - 1.0 : v;
+                        }
+#elif SDE_RNG == 2
+                        {   // digital shift: one 64-bit mask per dimension; 52-bit centred uniform
+                            const sde_u64 kb = ((((sde_u64)x) << 32) ^ __ldg(prm.xor_masks + d)) >> 12;
+                            u = ((double)(long long)kb + 0.5) * 2.220446049250313e-16;               // * 2^-52
+                        }
+#else
+                        u = (double)x * 2.3283064365386963e-10;                                      // x / 2^32
+#endif
+                        if (k == 0) u0 = u;
+                        zu[k] = sde_uniform_to_draw(u, sde_factor_is_wiener(k), s_icdf, lane);
+                    }
+#endif
+                    sde_model_step(row, cache, ct, zu, u0, __ldg(prm.times + t), __ldg(prm.times + t + 1),
+                                   __ldg(prm.dts + t), __ldg(prm.sqrt_dts + t));
+#if SDE_OUT == 0
+#pragma unroll
+                    for (int p = 0; p < SDE_P; ++p) my_tile[(t - t0) * SDE_P + p] = row[p];
+#elif SDE_OUT == 1
+                    if (valid) {
+#pragma unroll
+                        for (int p = 0; p < SDE_P; ++p)
+                            prm.out[((size_t)(t + 1) * SDE_P + p) * prm.n_paths + s_local] = row[p];
+                    }
+#endif
+                }
+            }
+        }
+#if SDE_OUT == 0
+        // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
+        __syncwarp();
+        {
+            const int ncols = (t_end - t0) * SDE_P;
+            const double* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                if ((valid_mask >> r) & 1u) {
+                    double* dst = prm.out + ((size_t)(s_warp0 + r) * T + (t0 + 1)) * SDE_P;
+                    for (int i = lane; i < ncols; i += 32) dst[i] = wt[r * SDE_TILE_LD + i];
+                }
+            }
+        }
+        __syncwarp();
+#endif
+    }
+
+#if SDE_OUT == 2
+    if (valid) {
+#pragma unroll
+        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)s_local * SDE_P + p] = row[p];
+    }
+#elif SDE_OUT == 3
+    // warp-shuffle + block reduction of (count, mean, M2) per process; fixed order => deterministic
+    for (int p = 0; p < SDE_P; ++p) {
+        SdeMoments m;
+        m.n = valid ? 1.0 : 0.0; m.mean = valid ? row[p] : 0.0; m.m2 = 0.0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            SdeMoments o;
+            o.n = __shfl_xor_sync(0xffffffffu, m.n, off);
+            o.mean = __shfl_xor_sync(0xffffffffu, m.mean, off);
+            o.m2 = __shfl_xor_sync(0xffffffffu, m.m2, off);
+            // merge in a lane-independent order so every lane holds the same bits
+            m = ((lane & off) == 0) ? sde_mom_merge(m, o) : sde_mom_merge(o, m);
+        }
+        __syncthreads();
+        if (lane == 0) { s_mom[warp * 3 + 0] = m.n; s_mom[warp * 3 + 1] = m.mean; s_mom[warp * 3 + 2] = m.m2; }
+        __syncthreads();
+        if (tid == 0) {
+            SdeMoments acc; acc.n = s_mom[0]; acc.mean = s_mom[1]; acc.m2 = s_mom[2];
+            for (int w = 1; w < SDE_NW; ++w) {
+                SdeMoments o; o.n = s_mom[w * 3]; o.mean = s_mom[w * 3 + 1]; o.m2 = s_mom[w * 3 + 2];
+                acc = sde_mom_merge(acc, o);
+            }
+            double* dst = prm.partials + ((size_t)blockIdx.x * SDE_P + p) * 3;
+            dst[0] = acc.n; dst[1] = acc.mean; dst[2] = acc.m2;
+        }
+    }
+#endif
+}
+
+// Second stage of the moment reduction: one CTA folds [n_partials][P][3] -> [P][3], fixed order.
+extern "C" __global__ void __launch_bounds__(256) sde_moments_finalize(const double* __restrict__ partials, sde_u64 n_partials,
+                                                                        double* __restrict__ out) {
+    __shared__ double s[256 * 3];
+    const int tid = threadIdx.x;
+    for (int p = 0; p < SDE_P; ++p) {
+        SdeMoments acc; acc.n = 0.0; acc.mean = 0.0; acc.m2 = 0.0;
+        for (sde_u64 i = tid; i < n_partials; i += 256) {
+            const double* src = partials + (i * SDE_P + p) * 3;
+            SdeMoments o; o.n = src[0]; o.mean = src[1]; o.m2 = src[2];
+            acc = sde_mom_merge(acc, o);
+        }
+        __syncthreads();
+        s[tid * 3] = acc.n; s[tid * 3 + 1] = acc.mean; s[tid * 3 + 2] = acc.m2;
+        __syncthreads();
+        for (int stride = 128; stride > 0; stride >>= 1) {
+            if (tid < stride) {
+                SdeMoments a, b;
+                a.n = s[tid * 3]; a.mean = s[tid * 3 + 1]; a.m2 = s[tid * 3 + 2];
+                b.n = s[(tid + stride) * 3]; b.mean = s[(tid + stride) * 3 + 1]; b.m2 = s[(tid + stride) * 3 + 2];
+                a = sde_mom_merge(a, b);
+                s[tid * 3] = a.n; s[tid * 3 + 1] = a.mean; s[tid * 3 + 2] = a.m2;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { out[p * 3] = s[0]; out[p * 3 + 1] = s[1]; out[p * 3 + 2] = s[2]; }
+    }
+}

@@ -1,0 +1,87 @@
+// sde_util_kernels.cu — model-independent kernels, compiled ahead of time for sm_100a
+// (nvcc -cubin) and embedded in libsde_b200.so.  They expose each building block of the
+// fused kernel on its own so that every one has its own parity test, and hold the
+// microbenchmarks whose results sit beside MEASURED_PEAKS.json.
+#include "sde_device_rng.cuh"
+#include "sde_device_icdf.cuh"
+
+// K1: integer Sobol points out[i][d] (u64, low 32 bits zero) for n = first + i.
+// Same decomposition as the fused kernel: CTA-uniform part in shared memory, lane part from
+// the x_d(lane) table.  Replaces sobol::Sobol::next (src/rng/sobol.rs:23-25).
+extern "C" __global__ void __launch_bounds__(256) sde_k_sobol_points(const sde_u32* __restrict__ V, const sde_u32* __restrict__ lane_tab,
+                                                                      sde_u32 dims, sde_u64 n_base, sde_u64 first, sde_u64 count,
+                                                                      sde_u64* __restrict__ out) {
+    extern __shared__ sde_u32 s_bw[];                    // [dims_tile][8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const sde_u64 n_cta = n_base + (sde_u64)blockIdx.x * 256;
+    const sde_u64 n = n_cta + tid;
+    const bool valid = n >= first && n - first < count;
+    const sde_u32 DT = 256;                              // dimensions per tile
+    for (sde_u32 d0 = 0; d0 < dims; d0 += DT) {
+        const sde_u32 nd = min(DT, dims - d0);
+        __syncthreads();
+        for (sde_u32 e = tid; e < nd * 8; e += 256) {
+            const sde_u32 dl = e >> 3, w = e & 7;
+            s_bw[e] = sde_sobol_point32(V + (size_t)(d0 + dl) * 32, (sde_u32)n_cta + 32u * w);
+        }
+        __syncthreads();
+        if (valid) {
+            for (sde_u32 dl = 0; dl < nd; ++dl) {
+                const sde_u32 x = s_bw[dl * 8 + warp] ^ __ldg(lane_tab + (size_t)(d0 + dl) * 32 + lane);
+                out[(n - first) * dims + d0 + dl] = ((sde_u64)x) << 32;
+            }
+        }
+    }
+}
+
+// K2: first n u64 outputs of ChaCha8Rng::seed_from_u64(seed); thread i produces block i.
+extern "C" __global__ void sde_k_chacha8_u64(sde_u64 seed, sde_u64 n, sde_u64* __restrict__ out) {
+    const sde_u64 b = (sde_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b * 8 >= n) return;
+    sde_u32 key[8], buf[16];
+    sde_seed_from_u64(seed, key);
+    sde_chacha_block<8>(key, b, buf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (b * 8 + i < n) out[b * 8 + i] = ((sde_u64)buf[2 * i + 1] << 32) | buf[2 * i];
+}
+
+// K3: inverse normal CDF, both evaluations.
+extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal(const double* __restrict__ p, sde_u64 n, int mode, double* __restrict__ out) {
+    __shared__ double4 s_raw[SDE_ICDF_TABLE_DOUBLES / 4];
+    double* s_table = reinterpret_cast<double*>(s_raw);
+    sde_icdf_table_load(s_table, threadIdx.x, 256);
+    __syncthreads();
+    const sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    out[i] = mode == 1 ? sde_icdf_normal_fast(p[i], s_table, threadIdx.x & 31) : sde_icdf_normal_reference(p[i]);
+}
+
+extern "C" __global__ void sde_k_icdf_poisson(const double* __restrict__ u, const double* __restrict__ lambda, sde_u64 n, double* __restrict__ out) {
+    const sde_u64 i = (sde_u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sde_icdf_poisson(u[i], lambda[i]);
+}
+
+// ---- microbenchmarks ------------------------------------------------------------------
+// pure-write bandwidth: 16-byte stores, grid-stride
+extern "C" __global__ void __launch_bounds__(256) sde_k_fill(double2* __restrict__ dst, sde_u64 n_vec, double v) {
+    const sde_u64 stride = (sde_u64)gridDim.x * 256;
+    for (sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += stride) dst[i] = make_double2(v, v);
+}
+// FP64 FMA issue peak: 8 independent chains per thread
+extern "C" __global__ void __launch_bounds__(256) sde_k_dfma(double* __restrict__ out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * 256 + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+extern "C" __global__ void __launch_bounds__(256) sde_k_ffma(float* __restrict__ out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * 256 + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}

@@ -1,0 +1,337 @@
+"""sde_sim_rs — B200-native drop-in for the simulation hot path of Aschii85/sde-sim-rs.
+
+Mirrors the reference's Python surface (python/sde_sim_rs/__init__.py:1-3 re-exporting the
+pyo3 function src/py_binding.rs:8-56):
+
+    simulate(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme)
+
+Same argument names, meaning and errors (ValueError for scenarios <= 0 and unparsable
+equations, RuntimeError for simulation failures).  The reference returns a polars
+DataFrame in long format; polars is not importable here, so `simulate` returns a
+`Filtration` that holds the dense value tensor on the GPU and renders the same long-format
+columns (scenario:i32, time:f64, process_name:str, value:f64; src/filtration.rs:108-113) on
+request (`.columns()`, `.to_pandas()`, `.to_polars()` when polars exists).
+
+Everything runs through libsde_b200.so (hand-written sm_100a CUDA behind a C-ABI).  PyTorch is
+used only for device memory, streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import (ARITH_FAST, ARITH_STRICT, ICDF_FAST, ICDF_REFERENCE, LAYOUT_NTP, LAYOUT_TPN, OUT_MOMENTS,
+                   OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
+                   SCRAMBLE_XOR)
+
+__all__ = ["simulate", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
+           "cuda_available", "version"]
+
+_OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
+_LAYOUTS = {"NTP": LAYOUT_NTP, "TPN": LAYOUT_TPN}
+_SCRAMBLES = {"cp_shift_per_path": SCRAMBLE_CP_SHIFT_PER_PATH, "xor": SCRAMBLE_XOR, "none": SCRAMBLE_NONE}
+_ICDFS = {"reference": ICDF_REFERENCE, "fast": ICDF_FAST}
+_ARITHS = {"strict": ARITH_STRICT, "fast": ARITH_FAST}
+_RKS = {"reference": RK_REFERENCE, "textbook": RK_TEXTBOOK}
+
+
+def version() -> str:
+    return _ffi.lib().sde_version().decode()
+
+
+def cuda_available() -> bool:
+    return bool(_ffi.lib().sde_cuda_available())
+
+
+def _pick(table: dict, key: str, what: str) -> int:
+    try:
+        return table[key]
+    except KeyError:
+        raise ValueError(f"unknown {what} {key!r}; expected one of {sorted(table)}") from None
+
+
+class Universe:
+    """proc::ProcessUniverse (src/proc/mod.rs:61-90) built by proc::util::parse_equations."""
+
+    def __init__(self, processes_equations: Sequence[str], time_steps: Sequence[float]):
+        L = _ffi.lib()
+        self.equations = [str(e) for e in processes_equations]
+        self.time_steps = np.ascontiguousarray(np.asarray(time_steps, dtype=np.float64))
+        h = C.c_void_p()
+        rc = L.sde_universe_parse(_ffi.cstr_array(self.equations), len(self.equations),
+                                  self.time_steps.ctypes.data_as(C.c_void_p), self.time_steps.size, C.byref(h))
+        _ffi.check(rc, prefix_value="Failed to parse equations: ")          # py_binding.rs:30-32
+        self._h = h
+        self.num_processes = L.sde_universe_num_processes(h)
+        self.num_factors = L.sde_universe_num_factors(h)
+        self.process_names = [L.sde_universe_process_name(h, i).decode() for i in range(self.num_processes)]
+        self.is_levy = [bool(L.sde_universe_process_is_levy(h, i)) for i in range(self.num_processes)]
+        self.num_terms = [L.sde_universe_process_num_terms(h, i) for i in range(self.num_processes)]
+        self.factor_names = [L.sde_universe_factor_name(h, k).decode() for k in range(self.num_factors)]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _ffi._lib is not None:
+            _ffi._lib.sde_universe_free(h)
+
+
+def parse_equations(processes_equations: Sequence[str], time_steps: Sequence[float]) -> Universe:
+    """proc::util::parse_equations (src/proc/util.rs:52-66)."""
+    return Universe(processes_equations, time_steps)
+
+
+def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, layout: str, scramble: str, icdf: str,
+                  arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0):
+    o = _ffi.default_options()
+    o.device = device
+    o.seed = seed & (2**64 - 1)
+    o.scenario_offset = scenario_offset
+    o.output = _pick(_OUTPUTS, output, "output")
+    o.layout = _pick(_LAYOUTS, layout, "layout")
+    o.scramble = _pick(_SCRAMBLES, scramble, "scramble")
+    o.icdf = _pick(_ICDFS, icdf, "icdf")
+    o.arith = _pick(_ARITHS, arithmetic, "arithmetic")
+    o.rk_variant = _pick(_RKS, rk_variant, "rk_variant")
+    o.inject = inject_ptr or None
+    o.tile_steps = tile_steps
+    o.block_threads = block_threads
+    return o
+
+
+def _current_device() -> int:
+    import torch
+
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+class Plan:
+    """One model lowered to sm_100a device code for one (scheme, rng_method, options) choice."""
+
+    def __init__(self, universe: Universe, scheme: str = "euler", rng_method: str = "pseudo", *, output: str = "paths",
+                 layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
+                 arithmetic: str = "strict", rk_variant: str = "reference", device: Optional[int] = None,
+                 inject=None, tile_steps: int = 0, block_threads: int = 0):
+        self.universe = universe
+        self.scheme, self.rng_method = scheme, rng_method
+        self.output, self.layout = output, layout
+        self.device = _current_device() if device is None else int(device)
+        self._inject = inject                                   # keep the tensor alive
+        opts = _make_options(device=self.device, seed=0, scenario_offset=0, output=output, layout=layout,
+                             scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant,
+                             inject_ptr=(inject.data_ptr() if inject is not None else 0), tile_steps=tile_steps,
+                             block_threads=block_threads)
+        h = C.c_void_p()
+        rc = _ffi.lib().sde_plan_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), C.byref(h))
+        _ffi.check(rc, prefix_runtime="Simulation failed: ")
+        self._h = h
+        self.launches = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _ffi._lib is not None:
+            _ffi._lib.sde_plan_free(h)
+
+    @property
+    def source(self) -> str:
+        return _ffi.lib().sde_plan_source(self._h).decode()
+
+    def output_shape(self, scenarios: int):
+        T, P = self.universe.time_steps.size, self.universe.num_processes
+        if self.output == "paths":
+            return (scenarios, T, P) if self.layout == "NTP" else (T, P, scenarios)
+        if self.output == "terminal":
+            return (scenarios, P)
+        return (P, 3)
+
+    @staticmethod
+    def _init_arrays(initial_values: Dict[str, float]):
+        names = list(initial_values)
+        vals = np.asarray([float(initial_values[k]) for k in names], dtype=np.float64)
+        return _ffi.cstr_array(names), vals, len(names)
+
+    def run(self, initial_values: Dict[str, float], scenarios: int, *, seed: int = 0, scenario_offset: int = 0,
+            out=None, stream=None):
+        """Launch on the current torch stream; returns a CUDA float64 tensor (device resident)."""
+        import torch
+
+        if scenarios <= 0:
+            raise ValueError("scenarios must be a positive integer")
+        shape = self.output_shape(scenarios)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float64, device=f"cuda:{self.device}")
+        elif tuple(out.shape) != tuple(shape) or out.dtype != torch.float64 or not out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CUDA float64 tensor of shape {shape}")
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        names, vals, n = self._init_arrays(initial_values)
+        nl = C.c_int(0)
+        rc = _ffi.lib().sde_plan_run_device(self._h, names, vals.ctypes.data_as(C.c_void_p), n, scenarios,
+                                            seed & (2**64 - 1), scenario_offset, C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(stream), C.byref(nl))
+        _ffi.check(rc, prefix_runtime="Simulation failed: ")
+        self.launches += nl.value
+        return out
+
+    def run_host(self, initial_values: Dict[str, float], scenarios: int, *, seed: int = 0, scenario_offset: int = 0,
+                 out=None):
+        """HOST buffers end to end: device memory managed by the library, chunked D2H overlapped with compute.
+
+        `out` may be a numpy array or a (pinned) CPU torch tensor; returns it."""
+        if scenarios <= 0:
+            raise ValueError("scenarios must be a positive integer")
+        shape = self.output_shape(scenarios)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        if int(np.prod(out.shape)) != int(np.prod(shape)):
+            raise ValueError(f"out must hold {shape} float64 values")
+        names, vals, n = self._init_arrays(initial_values)
+        nl = C.c_int(0)
+        rc = _ffi.lib().sde_plan_run_host(self._h, names, vals.ctypes.data_as(C.c_void_p), n, scenarios,
+                                          seed & (2**64 - 1), scenario_offset, C.c_void_p(ptr), C.byref(nl))
+        _ffi.check(rc, prefix_runtime="Simulation failed: ")
+        self.launches += nl.value
+        return out
+
+
+class Filtration:
+    """Result of `simulate`: the value column of every ScenarioFiltration (src/filtration.rs:12-19,112),
+    dense on the GPU, with the reference's long-format view built on request."""
+
+    def __init__(self, values, time_steps: np.ndarray, process_names: List[str], *, output: str, layout: str,
+                 scenario_offset: int = 0, seed: int = 0):
+        self.values = values                # torch.cuda tensor
+        self.time_steps = time_steps
+        self.process_names = process_names
+        self.output, self.layout = output, layout
+        self.scenario_offset = scenario_offset
+        self.seed = seed
+
+    @property
+    def shape(self):
+        return tuple(self.values.shape)
+
+    def dense(self):
+        """[N, T, P] view (reference row order) for full-path results."""
+        if self.output != "paths":
+            raise ValueError("dense() needs output='paths'")
+        return self.values if self.layout == "NTP" else self.values.permute(2, 0, 1)
+
+    def to_numpy(self) -> np.ndarray:
+        return self.values.detach().cpu().numpy()
+
+    def moments(self) -> Dict[str, Dict[str, float]]:
+        if self.output != "moments":
+            raise ValueError("moments() needs output='moments'")
+        m = self.to_numpy()
+        return {name: {"count": float(m[i, 0]), "mean": float(m[i, 1]), "m2": float(m[i, 2]),
+                       "variance": float(m[i, 2] / (m[i, 0] - 1)) if m[i, 0] > 1 else float("nan")}
+                for i, name in enumerate(self.process_names)}
+
+    def columns(self) -> Dict[str, np.ndarray]:
+        """The four columns of ScenarioFiltration::to_lazyframe concatenated over scenarios
+        (src/filtration.rs:87-113, src/sim/mod.rs:88-91): rows ordered (scenario, time, process)."""
+        dense = self.dense().detach().cpu().numpy()
+        N, T, P = dense.shape
+        scen = (np.arange(N, dtype=np.int64) + self.scenario_offset).astype(np.int32)     # `s_idx as i32` wraps (sim/mod.rs:47)
+        return {
+            "scenario": np.repeat(scen, T * P),
+            "time": np.tile(np.repeat(self.time_steps, P), N),
+            "process_name": np.tile(np.asarray(self.process_names, dtype=object), N * T),
+            "value": dense.reshape(-1),
+        }
+
+    def to_pandas(self):
+        import pandas as pd
+
+        return pd.DataFrame(self.columns())
+
+    def to_polars(self):
+        import polars as pl  # not in this image; present wherever the reference's callers run
+
+        c = self.columns()
+        return pl.DataFrame({"scenario": c["scenario"], "time": c["time"],
+                             "process_name": [str(x) for x in c["process_name"]], "value": c["value"]})
+
+
+_PLAN_CACHE: Dict[tuple, Plan] = {}
+
+
+def _cached_plan(equations, time_steps, scheme, rng_method, **kw) -> Plan:
+    ts = np.ascontiguousarray(np.asarray(time_steps, dtype=np.float64))
+    key = (tuple(equations), ts.tobytes(), scheme, rng_method, tuple(sorted(kw.items())))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = Plan(Universe(equations, ts), scheme, rng_method, **kw)
+        if len(_PLAN_CACHE) > 64:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
+             initial_values: Dict[str, float], rng_method: str = "pseudo", scheme: str = "euler", *,
+             seed: Optional[int] = None, output: str = "paths", layout: str = "NTP",
+             scramble: str = "cp_shift_per_path", icdf: str = "reference", arithmetic: str = "strict",
+             rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0) -> Filtration:
+    """Drop-in for sde_sim_rs.simulate (src/py_binding.rs:10-18; defaults as in python/sde_sim_rs/sde_sim_rs.pyi:11-12).
+
+    Keyword-only extensions: `seed` (the reference draws a fresh OS-entropy seed per call,
+    src/sim/mod.rs:28-29 — so does this when seed is None), `output` paths|terminal|moments, `layout`,
+    `scramble` cp_shift_per_path (reference behaviour) | xor | none, `icdf` reference|fast,
+    `arithmetic` strict|fast, `rk_variant` reference|textbook, `device`, `scenario_offset`.
+    """
+    if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
+        raise ValueError("scenarios must be a positive integer")                      # py_binding.rs:20-24
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    # parse first so that equation errors surface as ValueError before any CUDA work (py_binding.rs:30-32)
+    plan = _cached_plan(list(processes_equations), time_steps, scheme, rng_method, output=output, layout=layout,
+                        scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant, device=device)
+    values = plan.run(dict(initial_values), int(scenarios), seed=seed, scenario_offset=scenario_offset)
+    return Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output, layout=layout,
+                      scenario_offset=scenario_offset, seed=seed)
+
+
+# ---------------------------------------------------------------- multi-GPU helpers
+def shard_range(scenarios: int, rank: int, world_size: int):
+    """Scenario range [lo, hi) of `rank`: contiguous, disjoint, union = [0, scenarios).  Sobol point
+    indices and ChaCha keys are functions of the global scenario index, so the union of the shards is
+    bit-identical to a single-GPU run."""
+    base, rem = divmod(int(scenarios), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_moments(shards: np.ndarray) -> np.ndarray:
+    """[n_shards, P, 3] (count, mean, M2) -> [P, 3], Chan et al. merge in shard order (deterministic)."""
+    shards = np.ascontiguousarray(np.asarray(shards, dtype=np.float64))
+    n, P, three = shards.shape
+    assert three == 3
+    out = np.zeros((P, 3), dtype=np.float64)
+    _ffi.check(_ffi.lib().sde_moments_merge(shards.ctypes.data_as(C.c_void_p), n, P, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def simulate_sharded(processes_equations, time_steps, scenarios, initial_values, rng_method="pseudo", scheme="euler", *,
+                     seed: int = 0, output: str = "moments", **kw) -> Filtration:
+    """One process per GPU (torch.distributed already initialised): every rank simulates its scenario range;
+    moments are all-gathered (3·P doubles per rank over NCCL/NVLink) and merged identically on every rank;
+    paths / terminal values stay resident on their GPU."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    lo, hi = shard_range(scenarios, rank, world)
+    res = simulate(processes_equations, time_steps, hi - lo, initial_values, rng_method, scheme, seed=seed,
+                   output=output, scenario_offset=lo, **kw)
+    if output == "moments" and world > 1:
+        gathered = [torch.empty_like(res.values) for _ in range(world)]
+        dist.all_gather(gathered, res.values)
+        merged = merge_moments(torch.stack(gathered).cpu().numpy())
+        res.values = torch.from_numpy(merged).to(res.values.device)
+    return res

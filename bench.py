@@ -1,0 +1,291 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the SDE path-simulation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1], "C2"): 1-D GBM, Euler–Maruyama, RQMC scrambled Sobol,
+2^24 paths x 252 steps per GPU, full-path f64 output [N, 253, 1] (33.96 GB) left resident in HBM.
+A "step" is one pass of the hot path over that batch.  Multi-GPU: one process per GPU (torchrun),
+rank r simulates scenarios [r*2^24, (r+1)*2^24) — disjoint Sobol index ranges, no data-path collective —
+so scaling is weak and `value` is the aggregate path-steps/s.
+
+The JSON line carries `roofline` (HBM write bound; algorithmic bytes = 8*P per path-step incl. the t0 row),
+`cpu_baseline` (the CPU oracle on a bounded sample, on this box's host cores), `e2e` (same workload through
+the C-ABI host-buffer call: chunked simulate + D2H into pinned host memory inside the timed region),
+`clocks` and `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "sde-sim-rs_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GBM_EQ = ["dX1 = ( 0.05 * X1 ) * dt + ( 0.1 * X1) * dW1"]
+D = 252
+TIMES = [k / D for k in range(D + 1)]
+INIT = {"X1": 1.0}
+N_PER_GPU = 1 << 24
+SEED = 42
+METRIC = "path_steps_per_sec"
+UNIT = "path-steps/s"
+WORKLOAD = "C2: 1-D GBM Euler-Maruyama, RQMC scrambled Sobol (XOR digital shift), 2^24 paths x 252 steps per GPU, full-path f64 output [N,253,1]"
+
+
+def _measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic_bytes():
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(sample_paths: int, repeats: int = 1):
+    """The reference's CPU algorithm (oracle port, OpenMP over scenarios like rayon in src/sim/mod.rs:41-43)
+    on a bounded sample of the C2 workload.  Returns (path_steps_per_s, cores, seconds_per_pass)."""
+    from oracle import oracle as orc
+
+    orc.build()
+    U = orc.Universe(GBM_EQ, TIMES)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.simulate(U, INIT, sample_paths, "euler", "sobol", seed=SEED, scramble="xor")
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_paths * D / best, orc.num_threads(), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1 << 17
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    from oracle import oracle as orc
+
+    orc.build()
+    U = orc.Universe(GBM_EQ, TIMES)
+    for _ in range(min(W, 1)):
+        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor")
+    K = min(K, 5)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor")
+    dt = (time.perf_counter() - t0) / K
+    value = sample * D / dt
+    cores = orc.num_threads()
+    desc = f"{sample} paths x {D} steps of C2 per step (oracle C++ port of the reference algorithm, OpenMP, {cores} threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import sde_sim_rs as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    N, S_, P, T = args.paths, D, 1, D + 1
+    offset = rank * N
+
+    plan = S.Plan(S.Universe(GBM_EQ, TIMES), "euler", "sobol", output="paths", layout="NTP", scramble="xor",
+                  icdf=args.icdf, arithmetic=args.arithmetic, device=dev, tile_steps=args.tile_steps, block_threads=args.block)
+    out = torch.empty((N, T, P), dtype=torch.float64, device=f"cuda:{dev}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: `value`
+    for _ in range(args.warmup):
+        plan.run(INIT, N, seed=SEED, scenario_offset=offset, out=out)
+    barrier()
+    launches0 = plan.launches
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.run(INIT, N, seed=SEED, scenario_offset=offset, out=out)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    gpu_launches = plan.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * N * S_ / (ms_per_step * 1e-3)
+
+    # spot parity of what was just timed: first/last rows vs closed-form sanity (finite, positive, t0 row = x0)
+    chk = out[:4, :, 0].cpu()
+    assert torch.isfinite(chk).all() and bool((chk[:, 0] == 1.0).all())
+
+    # ---- end-to-end leg: host buffers through the C-ABI (sde_plan_run_host), D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        del out
+        torch.cuda.empty_cache()
+        nbytes = N * T * P * 8
+        try:
+            host = torch.empty((N, T, P), dtype=torch.float64, pin_memory=True)
+        except Exception as ex:  # noqa: BLE001
+            host = None
+            e2e = {"value": None, "unit": UNIT, "error": f"pinned host allocation of {nbytes} B failed: {ex}"}
+        if host is not None:
+            plan.run_host(INIT, N, seed=SEED, scenario_offset=offset, out=host)          # warm-up (also faults pages in)
+            barrier()
+            k2 = max(1, min(args.e2e_steps, args.steps))
+            t0 = time.perf_counter()
+            for _ in range(k2):
+                plan.run_host(INIT, N, seed=SEED, scenario_offset=offset, out=host)      # synchronous
+            barrier()
+            dt = (time.perf_counter() - t0) / k2
+            tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            assert float(host[0, 0, 0]) == 1.0 and bool(torch.isfinite(host[-1]).all())
+            e2e = {"value": world * N * S_ / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * P + 8 * S_ * 1,
+                   "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": k2,
+                   "api": "sde_plan_run_host (C-ABI, pinned host output, 512 MiB chunks, copy overlapped with compute)"}
+            del host
+
+    if rank == 0:
+        peak, peak_src = _measured_peak_gbs()
+        alg_bytes = N * T * P * 8
+        achieved = alg_bytes / (ms_per_step * 1e-3) * 1e-9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": _ncu_traffic_bytes(), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel": "sde_sim_kernel",
+                    "frac_of_8TBps_nominal": achieved / 8000.0}
+        cpu = None
+        if not args.no_cpu:
+            v, cores, secs = cpu_reference_leg(args.cpu_sample)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_sample} paths x {D} steps of C2, one pass ({secs:.1f} s), C++ oracle port, OpenMP"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "paths_per_gpu": N, "time_steps": S_, "processes": P, "seed": SEED,
+                       "rng": "sobol/xor", "icdf": args.icdf, "arithmetic": args.arithmetic, "layout": "NTP",
+                       "l2_policy": "each step writes 33.96 GB >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"paths sharded over {world} GPU(s), disjoint Sobol index ranges"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=N_PER_GPU)
+    ap.add_argument("--icdf", default="fast", choices=["fast", "reference"])
+    ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--tile-steps", type=int, default=0)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 17)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,11 +67,41 @@ class StepGen {
         return "sde_icdf_poisson(" + z + ", " + mul(lam, "dt") + ")";
     }
 
+    // coefficient j == lin[j] * X_p for every term (literal `c * X` or `X * c`), at most 128 terms
+    bool linear_in_own_state(const Process& pr, int p, double* lin) const {
+        if (pr.terms.empty() || pr.terms.size() > 128) return false;
+        for (size_t j = 0; j < pr.terms.size(); ++j) {
+            const Expr& e = pr.terms[j].coeff;
+            const ExprNode& r = e.nodes()[e.root()];
+            if (r.op != Op::Mul) return false;
+            const ExprNode& a = e.nodes()[r.args[0]];
+            const ExprNode& b = e.nodes()[r.args[1]];
+            if (a.op == Op::Const && b.op == Op::Var && b.var == p) lin[j] = a.value;
+            else if (b.op == Op::Const && a.op == Op::Var && a.var == p) lin[j] = b.value;
+            else return false;
+        }
+        // with a stale cache (steady state entered AT times[t]) c[p] is not X_p(t): keep the literal form
+        return true;
+    }
+
     void euler() {                                           // src/sim/euler.rs:5-37
         for (int p : u_.levy_indices) {
             const Process& pr = u_.processes[p];
             std::string sp = std::to_string(p);
             line("{   // Levy process " + sp + " '" + pr.name + "' (euler.rs:15-28)");
+            double lin[128];
+            if (!opt_.strict && linear_in_own_state(pr, p, lin)) {
+                // arithmetic=fast only: every coefficient is a_j * X_p, so X_p + sum (a_j X_p) dx_j = X_p * (1 + sum a_j dx_j):
+                // one FMA per term + one multiply instead of two multiplies + one FMA per term (<= ~2 ulp per step).
+                if (state_ != CUR && !pr.terms.empty()) refresh(CUR);
+                line("double g = 1.0;");
+                for (size_t j = 0; j < pr.terms.size(); ++j) {
+                    std::string x = increment(pr.terms[j]);
+                    line("g = fma(" + format_double(lin[j]) + ", " + x + ", g);");
+                }
+                line("n" + sp + " = row[" + sp + "] * g; }");   // Levy slots of the cache always equal row t in Euler
+                continue;
+            }
             line("double val = row[" + sp + "];");
             for (const Term& t : pr.terms) {
                 std::string cf = eval(t.coeff, CUR);
@@ -178,17 +208,23 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     if (tt <= 0) {
         tt = 32;
         if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 32 / P);
-        if (sobol) tt = std::min(tt, std::max(1, 512 / KK));
+        if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: tt*K*128 B of shared memory
     }
-    tt = std::max(L.ch, (tt / L.ch) * L.ch);
+    // steps unrolled per loop trip: whole ChaCha blocks, and >= 4 for small models so that loads, constants and
+    // the state-independent inverse-CDF chains of neighbouring steps overlap
+    L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
+    tt = std::max(L.unr, (tt / L.unr) * L.unr);
     L.tt = tt;
-    auto smem_for = [&](int block) {
+    auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;
-        size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)128 * 2 * 8 * 8 : 0;
+        size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
         size_t tile = (opt.out == OUT_PATHS_NTP) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
+        size_t step = (size_t)tt * 32;
+        size_t mask = (opt.rng == RNG_SOBOL_XOR) ? (size_t)tt * KK * 8 : 0;
         size_t bw = sobol ? (size_t)tt * KK * nw * 4 : 0;
+        size_t lane = sobol ? (size_t)tt * KK * 32 * 4 : 0;
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
-        return icdf + tile + bw + mom;
+        return icdf + tile + step + mask + bw + lane + mom;
     };
     if (opt.block <= 0) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
     L.smem_bytes = smem_for(L.block);
@@ -216,7 +252,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
-    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n";
+    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
     {

@@ -32,6 +32,7 @@ struct Lowered {
     int min_blocks = 1;
     int tt = 32;
     int ch = 1;
+    int unr = 1;             // steps unrolled per loop trip (multiple of ch)
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
     bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)
 };

@@ -13,6 +13,12 @@
 #pragma once
 #include "sde_icdf_tables.cuh"
 
+#ifndef SDE_TYPES_DEFINED
+#define SDE_TYPES_DEFINED
+typedef unsigned int sde_u32;
+typedef unsigned long long sde_u64;
+#endif
+
 #define SDE_AS_C0 2.515517
 #define SDE_AS_C1 0.802853
 #define SDE_AS_C2 0.010328
@@ -42,12 +48,16 @@ __device__ __forceinline__ double sde_rcp_approx(double a) {
     return r;
 }
 
-// Shared-memory copy of the log table.  REPL = 8 replicates every entry once per
-// 16-byte bank group so the 8 lanes of a quarter-warp never collide (LDS.128 = 4 clk/warp).
+// Shared-memory tables of the FAST path:
+//   [0, 128*2*REPL)  log table {1/c, -2 ln c}; REPL = 8 replicates every entry once per 16-byte bank
+//                    group so the 8 lanes of a quarter-warp never collide (LDS.128 = 4 clk/warp);
+//   then 64 doubles  eln2[h] = (h - 53) * (-2 ln 2): the exponent term for w = 1.m * 2^(h-53)
+//                    (avoids an int->f64 conversion per draw; lookups are bank-conflict free).
 #ifndef SDE_ICDF_TABLE_REPL
 #define SDE_ICDF_TABLE_REPL 8
 #endif
-#define SDE_ICDF_TABLE_DOUBLES (128 * 2 * SDE_ICDF_TABLE_REPL)
+#define SDE_ICDF_LOG_DOUBLES (128 * 2 * SDE_ICDF_TABLE_REPL)
+#define SDE_ICDF_TABLE_DOUBLES (SDE_ICDF_LOG_DOUBLES + 64)
 
 __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, int nthreads) {
     for (int i = tid; i < 128 * SDE_ICDF_TABLE_REPL; i += nthreads) {
@@ -55,15 +65,14 @@ __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, in
         s_table[2 * i] = sde_icdf_log_table[idx][0];
         s_table[2 * i + 1] = sde_icdf_log_table[idx][1];
     }
+    for (int h = tid; h < 64; h += nthreads) s_table[SDE_ICDF_LOG_DOUBLES + h] = (double)(h - 53) * -1.3862943611198906;
 }
 
-// w in (0, 0.5], normal.  Returns A&S x(w) >= ~0 (caller applies the sign).
-__device__ __forceinline__ double sde_icdf_normal_fast_core(double w, const double* s_table, int lane) {
-    const int hi = __double2hiint(w);
-    const int lo = __double2loint(w);
-    const int e = (hi >> 20) - 1023;
-    const int idx = (hi >> 13) & 0x7f;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+// Core: w = 1.mb * 2^(h-53) in (0, 0.5], given as mantissa bits mb (52 bits) and leading-one
+// position h of the 53-bit integer jw = w * 2^53.  Returns A&S x(w) (caller applies the sign).
+__device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, int h, const double* s_table, int lane) {
+    const int idx = mb_hi >> 13;                             // top 7 of the 52 mantissa bits
+    const double m = __hiloint2double((int)(mb_hi | 0x3ff00000u), (int)mb_lo);       // in [1, 2)
     const double2 tc = *reinterpret_cast<const double2*>(s_table + 2 * (idx * SDE_ICDF_TABLE_REPL + (lane & (SDE_ICDF_TABLE_REPL - 1))));
     const double r = fma(m, tc.x, -1.0);                    // |r| <= 2^-8
     // -2 log1p(r) = r * (-2 + r*(1 + r*(-2/3 + r*(1/2 + r*(-2/5)))))
@@ -71,9 +80,9 @@ __device__ __forceinline__ double sde_icdf_normal_fast_core(double w, const doub
     q = fma(q, r, -0.66666666666666663);
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
-    const double base = fma((double)e, -1.3862943611198906, tc.y);   // e * (-2 ln 2) - 2 ln c
+    const double base = s_table[SDE_ICDF_LOG_DOUBLES + h] + tc.y;      // (h-53) * (-2 ln 2) - 2 ln c
     const double w2 = fma(q, r, base);                      // -2 ln w  in [1.386, 73.5]
-    // t = sqrt(w2): seed y0 ~ w2^-1/2 (rel 2^-22.9), cubic correction -> rel ~2^-67
+    // t = sqrt(w2): seed y0 ~ w2^-1/2 (rel 2^-22.9), one cubic correction -> rel ~2^-66
     const double y0 = sde_rsqrt_approx(w2);
     const double g = w2 * y0;
     const double es = fma(-g, y0, 1.0);
@@ -88,10 +97,28 @@ __device__ __forceinline__ double sde_icdf_normal_fast_core(double w, const doub
     return t - quo;
 }
 
+// p = j * 2^-53, j a 53-bit integer (every uniform the on-device generators produce has this
+// form: rand's f64 is (u64 >> 11) * 2^-53, the digital-shift uniform is (2k+1) * 2^-53).
+// min(p, 1-p), the exponent/mantissa split and the sign all happen in the integer pipe.
+__device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const double* s_table, int lane) {
+    const bool upper = (j >> 52) != 0;                       // p >= 0.5  (increment.rs:165-169 uses 1 - p there)
+    const sde_u64 jw = upper ? (0x20000000000000ull - j) : j;   // exact 1 - p
+    const int h = 63 - __clzll((long long)jw);               // jw in [1, 2^52]
+    const sde_u64 mb = (jw << (52 - h)) & 0xfffffffffffffull;
+    double x = sde_icdf_as_core((sde_u32)(mb >> 32), (sde_u32)mb, h, s_table, lane);
+    int xhi = __double2hiint(x);
+    xhi ^= upper ? 0 : 0x80000000;                           // p < 0.5 -> -x
+    xhi = (j == 0) ? 0x7ff80000 : xhi;                       // ln(0) path of the reference -> NaN
+    return __hiloint2double(xhi, __double2loint(x));
+}
+
+// General f64 entry (Cranley–Patterson compat mode, stand-alone kernel): p in [0, 1).
 __device__ __forceinline__ double sde_icdf_normal_fast(double p, const double* s_table, int lane) {
     const bool lower = p < 0.5;
     const double w = lower ? p : 1.0 - p;                   // exact for every p the generators produce
-    double x = sde_icdf_normal_fast_core(w, s_table, lane);
+    const int hi = __double2hiint(w);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;              // w = 1.m * 2^e, e in [-53, -1]
+    double x = sde_icdf_as_core((sde_u32)hi & 0x000fffffu, (sde_u32)__double2loint(w), min(max(e + 53, 0), 63), s_table, lane);
     if (!(w > 0.0)) x = __longlong_as_double(0x7ff8000000000000ll);   // p = 0 -> NaN like ln(0) in the reference
     return lower ? -x : x;
 }

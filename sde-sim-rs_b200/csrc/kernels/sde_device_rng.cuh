@@ -13,8 +13,11 @@
 // Compiles under both nvcc and NVRTC (no host headers).
 #pragma once
 
+#ifndef SDE_TYPES_DEFINED
+#define SDE_TYPES_DEFINED
 typedef unsigned int sde_u32;
 typedef unsigned long long sde_u64;
+#endif
 
 // ---------------------------------------------------------------- ChaCha8 -------------
 __device__ __forceinline__ sde_u32 sde_rotl32(sde_u32 x, int r) { return __funnelshift_l(x, x, r); }

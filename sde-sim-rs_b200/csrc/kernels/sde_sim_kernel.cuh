@@ -53,12 +53,20 @@ struct SdeParams {
 // leading dimension of a warp's staging row: odd => conflict-free column writes
 #define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
 
-// shared-memory carve-up (bytes); mirrored by the host in engine.cpp via the same macros
+// shared-memory carve-up (bytes); mirrored by the host in lower.cpp
+//   icdf tables | output staging tile | per-tile step data {t, t+dt, dt, sqrt_dt} | Sobol: CTA/warp part,
+//   lane part and XOR masks of the tile's dimensions | moment scratch
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
 #define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
+#define SDE_SMEM_STEP_BYTES (SDE_TT * 32)
+#define SDE_SMEM_MASK_BYTES ((SDE_RNG == 2) ? (SDE_TT * SDE_KK * 8) : 0)
 #define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * SDE_NW * 4) : 0)
+#define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * 32 * 4) : 0)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_MOM_BYTES)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_MASK_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES + SDE_SMEM_MOM_BYTES)
+#ifndef SDE_UNR
+#define SDE_UNR SDE_CH
+#endif
 
 struct SdeMoments { double n, mean, m2; };
 
@@ -88,9 +96,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
     double* s_icdf = reinterpret_cast<double*>(smem);
     double* s_tile = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES);
-    sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES);
-    double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_BW_BYTES);
-    (void)s_icdf; (void)s_tile; (void)s_bw; (void)s_mom;
+    double* s_step = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES);
+    sde_u64* s_mask = reinterpret_cast<sde_u64*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES);
+    sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_MASK_BYTES);
+    sde_u32* s_lane = s_bw + (SDE_SMEM_BW_BYTES / 4);
+    double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_BYTES - SDE_SMEM_MOM_BYTES);
+    (void)s_icdf; (void)s_tile; (void)s_step; (void)s_mask; (void)s_bw; (void)s_lane; (void)s_mom;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -139,78 +150,129 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 
     for (int t0 = 0; t0 < S; t0 += SDE_TT) {
         const int t_end = min(t0 + SDE_TT, S);
-#if SDE_USES_SOBOL
-        // fold the CTA/warp part of the point index into shared memory for this tile's dimensions
+        // ---- tile prologue: everything the tile's steps read is staged in shared memory once per CTA
         __syncthreads();
+        for (int e = tid; e < (t_end - t0); e += SDE_BLOCK) {
+            const int t = t0 + e;
+            s_step[4 * e + 0] = __ldg(prm.times + t);
+            s_step[4 * e + 1] = __ldg(prm.times + t + 1);
+            s_step[4 * e + 2] = __ldg(prm.dts + t);
+            s_step[4 * e + 3] = __ldg(prm.sqrt_dts + t);
+        }
+#if SDE_USES_SOBOL
         {
             const int nd = (t_end - t0) * SDE_K;
+            const size_t d0 = (size_t)t0 * SDE_K;
+            // x_d(n_cta + 32 w): the CTA/warp part of the point index, folded once per CTA
             for (int e = tid; e < nd * SDE_NW; e += SDE_BLOCK) {
                 const int dl = e / SDE_NW, w = e - dl * SDE_NW;
-                const size_t d = (size_t)t0 * SDE_K + dl;
-                s_bw[e] = sde_sobol_point32(prm.sobol_V + d * 32, (sde_u32)n_cta + 32u * (sde_u32)w);
+                s_bw[e] = sde_sobol_point32(prm.sobol_V + (d0 + dl) * 32, (sde_u32)n_cta + 32u * (sde_u32)w);
             }
-        }
-        __syncthreads();
+            // x_d(lane): contiguous slice of the global lane table
+            for (int e = tid; e < nd * 32; e += SDE_BLOCK) s_lane[e] = __ldg(prm.sobol_lane + d0 * 32 + e);
+#if SDE_RNG == 2
+            for (int e = tid; e < nd; e += SDE_BLOCK) s_mask[e] = __ldg(prm.xor_masks + d0 + e);
 #endif
-        for (int tc = t0; tc < t_end; tc += SDE_CH) {
-#pragma unroll
-            for (int j = 0; j < SDE_CH; ++j) {
-                const int t = tc + j;
-                if (t < t_end) {
-                    double zu[SDE_KK];
-                    double u0 = 0.0;
-                    zu[0] = 0.0;
+        }
+#endif
+        __syncthreads();
+        // A group of SDE_UNR steps runs in two phases so that the scheduler sees SDE_UNR independent
+        // inverse-CDF chains side by side (they do not depend on the state) before the sequential state update:
+        //   draw(t, j, ..)    uniforms -> normal / Poisson draws of step t (j = position in the group; it must be a
+        //                     compile-time constant after unrolling so the ChaCha buffer is indexed statically)
+        //   advance(t, ..)    one step of the scheme + staging of the new row
+        auto draw = [&](const int t, const int j, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+            const int tl = t - t0;
+            u0 = 0.0;
+            zu[0] = 0.0;
+            (void)tl; (void)j;
 #if SDE_RNG == 4
-                    {
-                        const double* src = prm.inject + ((size_t)(valid ? s_local : 0) * S + t) * (SDE_K + 1);
+            {
+                const double* src = prm.inject + ((size_t)(valid ? s_local : 0) * S + t) * (SDE_K + 1);
 #pragma unroll
-                        for (int k = 0; k < SDE_K; ++k) zu[k] = __ldg(src + k);
-                        u0 = __ldg(src + SDE_K);
-                    }
+                for (int k = 0; k < SDE_K; ++k) zu[k] = __ldg(src + k);
+                u0 = __ldg(src + SDE_K);
+            }
 #else
 #pragma unroll
-                    for (int k = 0; k < SDE_K; ++k) {
-                        double u;
+            for (int k = 0; k < SDE_K; ++k) {
 #if SDE_USES_CHACHA
-                        const int slot = (j * SDE_K + k) & 7;      // compile-time after unrolling
-                        if (slot == 0) cha.refill();
-                        const double uc = (double)(long long)cha.bits53(slot) * 1.1102230246251565e-16;   // * 2^-53
+                const int slot = (j * SDE_K + k) & 7;      // compile-time after unrolling
+                if (slot == 0) cha.refill();
+                const sde_u64 jc = cha.bits53(slot);       // rand: f64 = (next_u64 >> 11) * 2^-53
 #endif
 #if SDE_USES_SOBOL
-                        const size_t d = (size_t)t * SDE_K + k;
-                        const sde_u32 x = s_bw[((t - t0) * SDE_K + k) * SDE_NW + warp] ^ __ldg(prm.sobol_lane + d * 32 + lane);
+                const int dl = tl * SDE_K + k;
+                const sde_u32 x = s_bw[dl * SDE_NW + warp] ^ s_lane[dl * 32 + lane];
 #endif
+#if SDE_RNG == 0 || SDE_RNG == 2
+                // uniforms of the form j * 2^-53: stay in the integer pipe until the draw is needed
 #if SDE_RNG == 0
-                        u = uc;
-#elif SDE_RNG == 1
-                        {   // RandomShiftScrambler::scramble: (raw + shift).fract()   (sobol.rs:73-76)
-                            const double v = (double)x * 2.3283064365386963e-10 + uc;
-                            u = (v >= 1.0) ? v - 1.0 : v;
-                        }
-#elif SDE_RNG == 2
-                        {   // digital shift: one 64-bit mask per dimension; 52-bit centred uniform
-                            const sde_u64 kb = ((((sde_u64)x) << 32) ^ __ldg(prm.xor_masks + d)) >> 12;
-                            u = ((double)(long long)kb + 0.5) * 2.220446049250313e-16;               // * 2^-52
-                        }
+                const sde_u64 j53 = jc;
 #else
-                        u = (double)x * 2.3283064365386963e-10;                                      // x / 2^32
+                // digital shift: one 64-bit mask per dimension; u = ((x ^ mask) >> 12 + 1/2) * 2^-52 = (2k+1) * 2^-53
+                const sde_u64 j53 = ((((((sde_u64)x) << 32) ^ s_mask[dl]) >> 12) << 1) | 1ull;
 #endif
-                        if (k == 0) u0 = u;
-                        zu[k] = sde_uniform_to_draw(u, sde_factor_is_wiener(k), s_icdf, lane);
-                    }
+                if (k == 0 && SDE_NEEDS_U0) u0 = (double)(long long)j53 * 1.1102230246251565e-16;
+                if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1
+                    zu[k] = sde_icdf_normal_fast_j53(j53, s_icdf, lane);
+#else
+                    zu[k] = sde_icdf_normal_reference((double)(long long)j53 * 1.1102230246251565e-16);
 #endif
-                    sde_model_step(row, cache, ct, zu, u0, __ldg(prm.times + t), __ldg(prm.times + t + 1),
-                                   __ldg(prm.dts + t), __ldg(prm.sqrt_dts + t));
+                } else {
+                    zu[k] = (double)(long long)j53 * 1.1102230246251565e-16;
+                }
+#else
+                double u;
+#if SDE_RNG == 1
+                {   // RandomShiftScrambler::scramble: (raw + shift).fract()   (sobol.rs:73-76)
+                    const double v = (double)x * 2.3283064365386963e-10 + (double)(long long)jc * 1.1102230246251565e-16;
+                    u = (v >= 1.0) ? v - 1.0 : v;
+                }
+#else
+                u = (double)x * 2.3283064365386963e-10;                                      // x / 2^32
+#endif
+                if (k == 0) u0 = u;
+                zu[k] = sde_uniform_to_draw(u, sde_factor_is_wiener(k), s_icdf, lane);
+#endif
+            }
+#endif
+        };
+        auto advance = [&](const int t, const double (&zu)[SDE_KK], const double u0) __attribute__((always_inline)) {
+            const int tl = t - t0;
+            sde_model_step(row, cache, ct, zu, u0, s_step[4 * tl], s_step[4 * tl + 1], s_step[4 * tl + 2], s_step[4 * tl + 3]);
 #if SDE_OUT == 0
 #pragma unroll
-                    for (int p = 0; p < SDE_P; ++p) my_tile[(t - t0) * SDE_P + p] = row[p];
+            for (int p = 0; p < SDE_P; ++p) my_tile[tl * SDE_P + p] = row[p];
 #elif SDE_OUT == 1
-                    if (valid) {
+            if (valid) {
 #pragma unroll
-                        for (int p = 0; p < SDE_P; ++p)
-                            prm.out[((size_t)(t + 1) * SDE_P + p) * prm.n_paths + s_local] = row[p];
-                    }
+                for (int p = 0; p < SDE_P; ++p)
+                    prm.out[((size_t)(t + 1) * SDE_P + p) * prm.n_paths + s_local] = row[p];
+            }
 #endif
+        };
+        if (t_end - t0 == SDE_TT) {
+            // full tile: no guards inside the group
+#pragma unroll 1
+            for (int tc = t0; tc < t0 + SDE_TT; tc += SDE_UNR) {
+                double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
+#pragma unroll
+                for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
+#pragma unroll
+                for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
+            }
+        } else {
+#pragma unroll 1
+            for (int tc = t0; tc < t_end; tc += SDE_UNR) {
+#pragma unroll
+                for (int j = 0; j < SDE_UNR; ++j) {
+                    if (tc + j < t_end) {
+                        double zu[SDE_KK], u0;
+                        draw(tc + j, j, zu, u0);
+                        advance(tc + j, zu, u0);
+                    }
                 }
             }
         }
@@ -218,13 +280,24 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
         __syncwarp();
         {
-            const int ncols = (t_end - t0) * SDE_P;
             const double* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                if ((valid_mask >> r) & 1u) {
-                    double* dst = prm.out + ((size_t)(s_warp0 + r) * T + (t0 + 1)) * SDE_P;
-                    for (int i = lane; i < ncols; i += 32) dst[i] = wt[r * SDE_TILE_LD + i];
+            constexpr int NC = SDE_TT * SDE_P;                 // columns of a full tile
+            if (t_end - t0 == SDE_TT && valid_mask == 0xffffffffu) {
+                // full tile, all 32 paths live: flat index f -> (row r, column i) with compile-time NC
+                double* dst0 = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P;
+                const size_t row_stride = (size_t)T * SDE_P;
+#pragma unroll 8
+                for (int f = lane; f < 32 * NC; f += 32) {
+                    const int r = f / NC, i = f - r * NC;
+                    dst0[(size_t)r * row_stride + i] = wt[r * SDE_TILE_LD + i];
+                }
+            } else {
+                const int ncols = (t_end - t0) * SDE_P;
+                for (int r = 0; r < 32; ++r) {
+                    if ((valid_mask >> r) & 1u) {
+                        double* dst = prm.out + ((size_t)(s_warp0 + r) * T + (t0 + 1)) * SDE_P;
+                        for (int i = lane; i < ncols; i += 32) dst[i] = wt[r * SDE_TILE_LD + i];
+                    }
                 }
             }
         }

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Tuning sweep on a GPU box: time the fused kernel on the C2 workload (reduced N) for a grid of
+(tile_steps, block_threads) and print path-steps/s; used to pick the lowering defaults."""
+import itertools
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sde-sim-rs_b200"))
+import sde_sim_rs as S  # noqa: E402
+
+GBM = ["dX1 = ( 0.05 * X1 ) * dt + ( 0.1 * X1) * dW1"]
+D = 252
+times = [k / D for k in range(D + 1)]
+N = int(os.environ.get("SWEEP_N", 1 << 22))
+modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="reference", arithmetic="strict")}
+which = sys.argv[1:] or ["fast"]
+out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
+res = []
+for mode in which:
+    for layout in ("NTP", "TPN"):
+        for tt, block in itertools.product((8, 16, 32), (128, 256)):
+            if layout == "TPN" and tt != 16:
+                continue
+            try:
+                plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", layout=layout, tile_steps=tt,
+                              block_threads=block, **modes[mode])
+                o = out if layout == "NTP" else out.view(D + 1, 1, N)
+                for _ in range(2):
+                    plan.run({"X1": 1.0}, N, seed=42, out=o)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    plan.run({"X1": 1.0}, N, seed=42, out=o)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                r = {"mode": mode, "layout": layout, "tt": tt, "block": block, "ms": ms, "gps": N * D / ms / 1e6,
+                     "gbs": N * (D + 1) * 8 / ms / 1e6}
+            except Exception as ex:  # noqa: BLE001
+                r = {"mode": mode, "layout": layout, "tt": tt, "block": block, "error": str(ex)[:200]}
+            print(json.dumps(r), flush=True)
+            res.append(r)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)

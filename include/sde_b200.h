@@ -63,12 +63,13 @@ enum sde_layout {
 };
 enum sde_scramble {
     SDE_SCRAMBLE_CP_SHIFT_PER_PATH = 0, /* reference behaviour: u = fract(x + ChaCha8(seed+s)) (src/rng/sobol.rs:45-47,73-76) */
-    SDE_SCRAMBLE_XOR = 1,               /* one 64-bit digital-shift mask per dimension per run (what README.md:13 describes)  */
+    SDE_SCRAMBLE_XOR = 1,               /* one 32-bit digital-shift mask per dimension per run on the 32-bit Sobol integers
+                                           (what README.md:13 describes): u = ((x ^ mask) + 1/2) * 2^-32                     */
     SDE_SCRAMBLE_NONE = 2
 };
 enum sde_icdf {
     SDE_ICDF_REFERENCE = 0, /* A&S 26.2.23 exactly as src/proc/increment.rs:161-179, IEEE log/sqrt/div, no contraction */
-    SDE_ICDF_FAST = 1       /* same formula; table-driven log + short Newton sqrt/div in f64; |dz| <= 2e-13 vs REFERENCE */
+    SDE_ICDF_FAST = 1       /* same formula; table-driven log + one-step Newton sqrt/div in f64; |dz| <= 5e-13 vs REFERENCE */
 };
 enum sde_arith {
     SDE_ARITH_STRICT = 0,   /* separate mul/add roundings in the reference's evaluation order       */

@@ -239,8 +239,8 @@ def uniforms(universe: Universe, scenarios: int, rng_method: str, *, seed: int =
         return (pts.astype(np.float64) * 2.0**-64).reshape(scenarios, S, K)
     if scramble == "xor":
         masks = chacha8_u64(seed, S * K)
-        k = (pts ^ masks[None, :]) >> np.uint64(12)
-        return ((k.astype(np.float64) + 0.5) * 2.0**-52).reshape(scenarios, S, K)
+        k = (pts ^ masks[None, :]) >> np.uint64(32)
+        return ((k.astype(np.float64) + 0.5) * 2.0**-32).reshape(scenarios, S, K)
     raw = pts.astype(np.float64) * 2.0**-64                 # exact for n < 2^53
     for s in range(scenarios):
         v = raw[s] + chacha8_f64(s + scenario_offset + seed, S * K)

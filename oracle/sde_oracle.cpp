@@ -690,11 +690,12 @@ struct SimOptions {
     int nthreads = 0;
 };
 
-// XOR digital shift (this build's own RQMC mode; not in the reference): per-dimension
-// 64-bit mask = u64 #d of ChaCha8Rng::seed_from_u64(seed); u = ((x ^ mask) >> 12 + 0.5) * 2^-52.
+// XOR digital shift (this build's own RQMC mode; README.md:13 describes it, the reference code does not
+// have it): the 32-bit Sobol integer (top half of the u64; exact for n < 2^32) is XORed with a per-dimension
+// 32-bit mask = top half of u64 #d of ChaCha8Rng::seed_from_u64(seed); u = (k + 1/2) * 2^-32.
 static inline double xor_uniform(uint64_t x, uint64_t mask) {
-    uint64_t k = (x ^ mask) >> 12;
-    return ((double)k + 0.5) * (1.0 / 4503599627370496.0);
+    uint64_t k = (x ^ mask) >> 32;
+    return ((double)k + 0.5) * (1.0 / 4294967296.0);
 }
 
 static inline double wiener_sample(Rng& rng, int t, int idx, double sqrt_dt, bool injected) {  // increment.rs:89-97

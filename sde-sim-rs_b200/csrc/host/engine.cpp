@@ -47,11 +47,12 @@ void joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit) {
         for (uint32_t i = 0; i < 18; ++i) minit[(size_t)d * 18 + i] = i < jk.stride ? jk.minit[(size_t)d * jk.stride + i] : 0;
 }
 
-void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane) {
+void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib) {
     const JoeKuo& jk = joe_kuo();
     if (dims > jk.ndims) throw ExprError{"Sobol dimension " + std::to_string(dims) + " exceeds the Joe-Kuo table (21201)"};
     V.assign((size_t)dims * 32, 0);
     lane.assign((size_t)dims * 32, 0);
+    if (nib) nib->assign((size_t)dims * 128, 0);
     for (uint32_t d = 0; d < dims; ++d) {
         uint32_t m[32];
         if (d == 0) {
@@ -73,6 +74,15 @@ void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>
             uint32_t g = l ^ (l >> 1), x = 0;
             for (int b = 0; b < 5; ++b) if ((g >> b) & 1u) x ^= Vd[b];
             Ld[l] = x;
+        }
+        if (nib) {
+            uint32_t* Nd = &(*nib)[(size_t)d * 128];
+            for (int i = 0; i < 8; ++i)
+                for (uint32_t v = 0; v < 16; ++v) {
+                    uint32_t x = 0;
+                    for (int b = 0; b < 4; ++b) if ((v >> b) & 1u) x ^= Vd[4 * i + b];
+                    Nd[i * 16 + v] = x;
+                }
         }
     }
 }
@@ -118,7 +128,7 @@ namespace {
 struct SdeParamsHost {   // must mirror SdeParams in csrc/kernels/sde_sim_kernel.cuh
     uint64_t n_paths, scen_offset, n_base, seed;
     int32_t n_steps, reserved;
-    CUdeviceptr times, dts, sqrt_dts, x0, sobol_V, sobol_lane, xor_masks, inject, out, partials;
+    CUdeviceptr times, dts, sqrt_dts, x0, sobol_nib, sobol_lane, xor_masks, inject, out, partials;
 };
 bool uses_sobol(int rng) { return rng == RNG_SOBOL_CP || rng == RNG_SOBOL_XOR || rng == RNG_SOBOL_RAW; }
 }  // namespace
@@ -146,11 +156,11 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
     d_sqrt_dts_.upload(sq.data(), sq.size() * 8);
     d_x0_.alloc((size_t)u_.P() * 8);
     if (uses_sobol(opt_.lower.rng) && dims > 0) {
-        std::vector<uint32_t> V, lane;
-        sobol_tables((uint32_t)dims, V, lane);
-        d_V_.upload(V.data(), V.size() * 4);
+        std::vector<uint32_t> V, lane, nib;
+        sobol_tables((uint32_t)dims, V, lane, &nib);
+        d_nib_.upload(nib.data(), nib.size() * 4);
         d_lane_.upload(lane.data(), lane.size() * 4);
-        if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 8);
+        if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 4);
     }
     cu_check(d.cuStreamCreate(&own_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     cu_check(d.cuStreamCreate(&copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
@@ -204,11 +214,14 @@ void Plan::set_initial_values(const std::vector<std::pair<std::string, double>>&
 void Plan::ensure_masks(uint64_t seed, CUstream stream) {
     if (opt_.lower.rng != RNG_SOBOL_XOR || d_masks_.bytes() == 0) return;
     if (masks_valid_ && masks_seed_ == seed) return;
-    std::vector<uint64_t> m(d_masks_.bytes() / 8);
-    chacha8_u64_host(seed, m.size(), m.data());
+    // digital-shift mask of dimension d = top 32 bits of u64 #d of ChaCha8Rng::seed_from_u64(seed)
+    std::vector<uint64_t> m64(d_masks_.bytes() / 4);
+    chacha8_u64_host(seed, m64.size(), m64.data());
+    std::vector<uint32_t> m(m64.size());
+    for (size_t i = 0; i < m.size(); ++i) m[i] = (uint32_t)(m64[i] >> 32);
     const DriverApi& d = driver();
     cu_check(d.cuStreamSynchronize(stream), "cuStreamSynchronize");
-    cu_check(d.cuMemcpyHtoD(d_masks_.ptr(), m.data(), m.size() * 8), "cuMemcpyHtoD(masks)");
+    cu_check(d.cuMemcpyHtoD(d_masks_.ptr(), m.data(), m.size() * 4), "cuMemcpyHtoD(masks)");
     masks_valid_ = true;
     masks_seed_ = seed;
 }
@@ -226,7 +239,7 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
     prm.seed = seed;
     prm.n_steps = u_.T() - 1;
     prm.times = d_times_.ptr(); prm.dts = d_dts_.ptr(); prm.sqrt_dts = d_sqrt_dts_.ptr(); prm.x0 = d_x0_.ptr();
-    prm.sobol_V = d_V_.ptr(); prm.sobol_lane = d_lane_.ptr(); prm.xor_masks = d_masks_.ptr();
+    prm.sobol_nib = d_nib_.ptr(); prm.sobol_lane = d_lane_.ptr(); prm.xor_masks = d_masks_.ptr();
     prm.inject = (CUdeviceptr)d_inject;
     prm.out = (CUdeviceptr)d_out;
     const uint64_t grid = (first_n + n - prm.n_base + block - 1) / block;

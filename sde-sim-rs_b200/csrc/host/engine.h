@@ -15,7 +15,9 @@ namespace sde {
 constexpr uint32_t kMaxSobolDims = 21201;
 void joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit /*[dims][18]*/);
 // V[d][b], b < 32: top 32 bits of the 64-bit direction numbers.  lane[d][l] = x_d(l), l < 32.
-void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane);
+// nib[d][i][v] (optional), i < 8, v < 16: XOR of V[d][4i+b] over the set bits b of v, so that
+// x_d(n) = XOR_i nib[d][i][(gray(n) >> 4i) & 15] — 8 independent loads instead of a bit loop.
+void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib = nullptr);
 // u64 #i of ChaCha8Rng::seed_from_u64(seed) (host copy, used for the XOR digital-shift masks)
 void chacha8_u64_host(uint64_t seed, size_t n, uint64_t* out);
 
@@ -52,7 +54,7 @@ class Plan {
     bool prelowered_ = false;
     CUmodule mod_ = nullptr;
     CUfunction fn_sim_ = nullptr, fn_fin_ = nullptr;
-    DeviceBuffer d_times_, d_dts_, d_sqrt_dts_, d_x0_, d_V_, d_lane_, d_masks_, d_partials_;
+    DeviceBuffer d_times_, d_dts_, d_sqrt_dts_, d_x0_, d_nib_, d_lane_, d_masks_, d_partials_;
     std::vector<double> x0_host_;
     bool masks_valid_ = false;
     uint64_t masks_seed_ = 0;

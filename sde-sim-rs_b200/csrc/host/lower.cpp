@@ -19,10 +19,15 @@ class StepGen {
   public:
     StepGen(const Universe& u, const LowerOptions& opt) : u_(u), opt_(opt) {}
 
+    // path-independent per-step constants hoisted into the tile prologue (arithmetic=fast only):
+    // each entry is a CUDA expression over t_cur, t_next, dt, sqrt_dt
+    std::vector<std::string> slots;
+
     // Emits the body of sde_model_step given the cache position on entry; returns it on exit.
     CacheAt generate(CacheAt enter, std::ostringstream& o) {
         state_ = enter;
         o_ = &o;
+        slots.clear();
         const int P = u_.P();
         for (int p = 0; p < P; ++p) line("double n" + std::to_string(p) + " = 0.0;");   // row t+1 is zero until set (filtration.rs:28)
         if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
@@ -91,11 +96,29 @@ class StepGen {
             line("{   // Levy process " + sp + " '" + pr.name + "' (euler.rs:15-28)");
             double lin[128];
             if (!opt_.strict && linear_in_own_state(pr, p, lin)) {
-                // arithmetic=fast only: every coefficient is a_j * X_p, so X_p + sum (a_j X_p) dx_j = X_p * (1 + sum a_j dx_j):
-                // one FMA per term + one multiply instead of two multiplies + one FMA per term (<= ~2 ulp per step).
+                // arithmetic=fast only: every coefficient is a_j * X_p, so
+                //   X_p + sum_j (a_j X_p) dx_j = X_p * (A + sum_k B_k z_k + sum_poisson a_j N_j),
+                //   A = 1 + sum_{dt terms} a_j dt,  B_k = (sum_{terms on dW_k} a_j) sqrt(dt)
+                // A and B_k do not depend on the path: they are computed once per step in the tile prologue
+                // (sde_model_step_consts) and read from shared memory.  <= ~3 ulp per step vs the literal order.
                 if (state_ != CUR && !pr.terms.empty()) refresh(CUR);
-                line("double g = 1.0;");
+                std::string A = "1.0";
+                std::vector<double> bsum(u_.K(), 0.0);
+                std::vector<bool> bused(u_.K(), false);
                 for (size_t j = 0; j < pr.terms.size(); ++j) {
+                    const Term& t = pr.terms[j];
+                    if (t.kind == IncKind::Time) A = "fma(" + format_double(lin[j]) + ", dt, " + A + ")";
+                    else if (t.kind == IncKind::Wiener) { bsum[t.factor] += lin[j]; bused[t.factor] = true; }
+                }
+                slots.push_back(A);
+                line("double g = ss[" + std::to_string(3 + slots.size()) + "];");
+                for (int k = 0; k < u_.K(); ++k) {
+                    if (!bused[k]) continue;
+                    slots.push_back("(" + format_double(bsum[k]) + " * sqrt_dt)");
+                    line("g = fma(ss[" + std::to_string(3 + slots.size()) + "], zu[" + std::to_string(k) + "], g);");
+                }
+                for (size_t j = 0; j < pr.terms.size(); ++j) {
+                    if (pr.terms[j].kind != IncKind::Poisson) continue;
                     std::string x = increment(pr.terms[j]);
                     line("g = fma(" + format_double(lin[j]) + ", " + x + ", g);");
                 }
@@ -201,14 +224,15 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     std::ostringstream body;
     StepGen gen(u, opt);
     gen.generate(L.enter_eq ? CUR : OLD, body);
+    const int nslot = (int)gen.slots.size();
 
     // ---- launch shape
     L.block = opt.block > 0 ? opt.block : 256;
     int tt = opt.tile_steps;
     if (tt <= 0) {
         tt = 32;
-        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 32 / P);
-        if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: tt*K*128 B of shared memory
+        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 16 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
+        if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
     }
     // steps unrolled per loop trip: whole ChaCha blocks, and >= 4 for small models so that loads, constants and
     // the state-independent inverse-CDF chains of neighbouring steps overlap
@@ -219,12 +243,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
         size_t tile = (opt.out == OUT_PATHS_NTP) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
-        size_t step = (size_t)tt * 32;
-        size_t mask = (opt.rng == RNG_SOBOL_XOR) ? (size_t)tt * KK * 8 : 0;
-        size_t bw = sobol ? (size_t)tt * KK * nw * 4 : 0;
-        size_t lane = sobol ? (size_t)tt * KK * 32 * 4 : 0;
+        size_t stage = (size_t)tt * (4 + nslot) * 8 + (sobol ? (size_t)tt * KK * nw * 4 + (size_t)tt * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
-        return icdf + tile + step + mask + bw + lane + mom;
+        return icdf + tile + 2 * stage + mom;
     };
     if (opt.block <= 0) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
     L.smem_bytes = smem_for(L.block);
@@ -252,7 +273,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
-    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n";
+    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
     {
@@ -263,8 +284,14 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "; }\n";
     s << "// one step of " << (opt.scheme == SCHEME_EULER ? "euler_iteration (src/sim/euler.rs:5-37)" : "runge_kutta_iteration (src/sim/runge_kutta.rs:5-107)")
       << "; cache enters " << (L.enter_eq ? "AT times[t] (stale values, not refreshed)" : "behind times[t] (refreshed at the first evaluation)") << "\n";
+    s << "// path-independent per-step constants, evaluated once per step in the tile prologue\n";
+    s << "__device__ __forceinline__ void sde_model_step_consts(const double t_cur, const double t_next, const double dt, const double sqrt_dt, double* slots) {\n";
+    s << "    (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)slots;\n";
+    for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << gen.slots[i] << ";\n";
+    s << "}\n";
     s << "__device__ __forceinline__ void sde_model_step(double (&row)[SDE_P], double (&c)[SDE_P], double& ct, const double (&zu)[SDE_KK],\n"
-         "                                               const double u0, const double t_cur, const double t_next, const double dt, const double sqrt_dt) {\n";
+         "                                               const double u0, const double* __restrict__ ss) {\n";
+    s << "    const double t_cur = ss[0], t_next = ss[1], dt = ss[2], sqrt_dt = ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
     s << body.str();
     s << "}\n#include \"sde_sim_kernel.cuh\"\n";

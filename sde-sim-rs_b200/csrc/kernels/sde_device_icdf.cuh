@@ -6,10 +6,10 @@
 //   REFERENCE  IEEE log / sqrt / divide and separately rounded mul/add in the reference's
 //              operation order.  Differs from the CPU oracle only by CUDA's log (<= 1 ulp)
 //              vs glibc's: |dz| <= 4 ulp(z) away from p = 0.5, <= 1e-15 absolute near it.
-//   FAST       table-driven log (128 x {1/c, -2 ln c}, degree-5 log1p), rsqrt.approx.f64 +
-//              one cubic correction, rcp.approx.f64 + one cubic correction, FMA Horner.
-//              ~22 FP64-pipe instructions instead of ~60.  Stated tolerance: |dz| <= 2e-13
-//              absolute vs REFERENCE over p in [2^-53, 1 - 2^-53] (measured: tests/test_icdf_gpu.py).
+//   FAST       table-driven log (128 x {1/c, -2 ln c}, degree-4 log1p), rsqrt.approx.f64 +
+//              one Newton step, rcp.approx.f64 + one Newton step, FMA Horner: 18 FP64-pipe
+//              instructions instead of ~60.  Stated tolerance: |dz| <= 5e-13 absolute vs
+//              REFERENCE over p in [2^-53, 1 - 2^-53] (measured: tests/test_gpu_blocks.py).
 #pragma once
 #include "sde_icdf_tables.cuh"
 
@@ -70,36 +70,39 @@ __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, in
 
 // Core: w = 1.mb * 2^(h-53) in (0, 0.5], given as mantissa bits mb (52 bits) and leading-one
 // position h of the 53-bit integer jw = w * 2^53.  Returns A&S x(w) (caller applies the sign).
+// 18 FP64-pipe instructions + 2 MUFU:
+//   -2 ln w   table {1/c, -2 ln c} on the top 7 mantissa bits, r = m/c - 1 (|r| <= 2^-8), degree-3 minimax
+//             polynomial for -2 log1p(r)/r (|err| <= 4.9e-14 absolute in -2 ln w)                         6
+//   sqrt      rsqrt.approx.f64 seed (rel 2^-22.9) + one Newton step (rel <= 2.4e-14)                     3
+//   N/D       Horner with FMA (2 + 3), rcp.approx.f64 seed + one Newton step (rel <= 1.4e-14), t - q    9
+// Stated tolerance of the whole map against the REFERENCE evaluation: |dz| <= 5e-13 absolute.
 __device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, int h, const double* s_table, int lane) {
     const int idx = mb_hi >> 13;                             // top 7 of the 52 mantissa bits
     const double m = __hiloint2double((int)(mb_hi | 0x3ff00000u), (int)mb_lo);       // in [1, 2)
     const double2 tc = *reinterpret_cast<const double2*>(s_table + 2 * (idx * SDE_ICDF_TABLE_REPL + (lane & (SDE_ICDF_TABLE_REPL - 1))));
-    const double r = fma(m, tc.x, -1.0);                    // |r| <= 2^-8
-    // -2 log1p(r) = r * (-2 + r*(1 + r*(-2/3 + r*(1/2 + r*(-2/5)))))
-    double q = fma(r, -0.4, 0.5);
-    q = fma(q, r, -0.66666666666666663);
+    const double r = fma(m, tc.x, -1.0);
+    double q = fma(r, 0x1.0000999a03338p-1, -0x1.55560888fbbc1p-1);
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
     const double base = s_table[SDE_ICDF_LOG_DOUBLES + h] + tc.y;      // (h-53) * (-2 ln 2) - 2 ln c
     const double w2 = fma(q, r, base);                      // -2 ln w  in [1.386, 73.5]
-    // t = sqrt(w2): seed y0 ~ w2^-1/2 (rel 2^-22.9), one cubic correction -> rel ~2^-66
+    // t = sqrt(w2): y0 ~ w2^-1/2; halve it in the integer pipe; t = g + g * (1 - g*y0)/2
     const double y0 = sde_rsqrt_approx(w2);
     const double g = w2 * y0;
-    const double es = fma(-g, y0, 1.0);
-    const double ps = fma(es, 0.375, 0.5);
-    const double t = fma(g, ps * es, g);
+    const double yh = __hiloint2double(__double2hiint(y0) - 0x00100000, 0);          // y0 / 2 (low word of the seed is 0)
+    const double es = fma(-g, yh, 0.5);
+    const double t = fma(g, es, g);
     const double num = fma(fma(SDE_AS_C2, t, SDE_AS_C1), t, SDE_AS_C0);
     const double den = fma(fma(fma(SDE_AS_D3, t, SDE_AS_D2), t, SDE_AS_D1), t, 1.0);
     const double r0 = sde_rcp_approx(den);
     const double ed = fma(-den, r0, 1.0);
     const double q0 = num * r0;
-    const double quo = fma(q0, fma(ed, ed, ed), q0);         // num/den, rel ~2^-69
+    const double quo = fma(q0, ed, q0);
     return t - quo;
 }
 
-// p = j * 2^-53, j a 53-bit integer (every uniform the on-device generators produce has this
-// form: rand's f64 is (u64 >> 11) * 2^-53, the digital-shift uniform is (2k+1) * 2^-53).
-// min(p, 1-p), the exponent/mantissa split and the sign all happen in the integer pipe.
+// p = j * 2^-53, j a 53-bit integer (rand's f64 is (u64 >> 11) * 2^-53).  min(p, 1-p), the
+// exponent/mantissa split and the sign all happen in the integer pipe.
 __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const double* s_table, int lane) {
     const bool upper = (j >> 52) != 0;                       // p >= 0.5  (increment.rs:165-169 uses 1 - p there)
     const sde_u64 jw = upper ? (0x20000000000000ull - j) : j;   // exact 1 - p
@@ -109,6 +112,20 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
     int xhi = __double2hiint(x);
     xhi ^= upper ? 0 : 0x80000000;                           // p < 0.5 -> -x
     xhi = (j == 0) ? 0x7ff80000 : xhi;                       // ln(0) path of the reference -> NaN
+    return __hiloint2double(xhi, __double2loint(x));
+}
+
+// p = (k + 1/2) * 2^-32, k = 32-bit digitally shifted Sobol integer: p = (2k+1) * 2^-33.
+// 1 - p = (2 ~k + 1) * 2^-33, so min(p, 1-p) is a conditional bit flip of k.
+__device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const double* s_table, int lane) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    const sde_u32 kw = k ^ (sde_u32)sgn;                     // top bit now clear; w = (2 kw + 1) * 2^-33
+    const int lz = __clz((int)kw);                           // 1..32 (32 when kw == 0: w = 2^-33 exactly)
+    // mantissa below the leading one of (kw:1), left aligned in 32 bits: shift in the centring bit, then zeros
+    sde_u32 mh = __funnelshift_lc(0x80000000u, kw, lz + 1);
+    mh = (kw == 0u) ? 0u : mh;
+    double x = sde_icdf_as_core(mh >> 12, mh << 20, 52 - lz, s_table, lane);          // w = 1.m * 2^(-1-lz): h - 53 = -1 - lz
+    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
     return __hiloint2double(xhi, __double2loint(x));
 }
 

@@ -9,18 +9,30 @@
 // generated device code (`sde_model_step`, emitted by csrc/host/lower.cpp from the parsed
 // equations) in the translation unit that includes this header.
 //
+// Structure of a CTA (SDE_BLOCK paths = SDE_NW warps):
+//   time is cut into tiles of SDE_TT steps.  Everything a tile's steps read — {t, t+dt, dt, sqrt(dt)} and
+//   model constants hoisted out of the path loop, the Sobol CTA/warp part x_d(n_cta + 32w) (with the
+//   digital-shift mask folded in) and the lane part x_d(lane) of the tile's dimensions — is staged in
+//   shared memory, double buffered: the loads for tile k+1 are issued before the last step group of tile k
+//   and land in registers while it computes; one __syncthreads per tile.
+//   Inside a tile, groups of SDE_UNR steps run in two phases: first the state-independent uniform ->
+//   normal chains of the whole group (independent instruction streams for the scheduler), then the
+//   sequential state updates.  Full paths are transposed through a per-warp shared-memory tile so that
+//   each path's [t0+1, t0+TT] x P segment leaves as contiguous 8-byte-coalesced stores.
+//
 // Macros expected from the generated prelude:
-//   SDE_P, SDE_K                   processes / stochastic factors
+//   SDE_P, SDE_K, SDE_KK           processes / stochastic factors / max(K, 1)
 //   SDE_RNG                        0 pseudo(ChaCha8)  1 sobol+per-path CP shift (reference)
 //                                  2 sobol+XOR digital shift  3 sobol raw  4 injected draws
 //   SDE_OUT                        0 paths [N][T][P]  1 paths [T][P][N]  2 terminal [N][P]  3 moments
 //   SDE_ICDF                       0 reference  1 fast
 //   SDE_NEEDS_U0                   1 when the scheme consumes u[t][0] directly (Runge–Kutta sk)
 //   SDE_BLOCK, SDE_MIN_BLOCKS      launch bounds
-//   SDE_TT                         time-tile length (multiple of SDE_CH)
-//   SDE_CH                         ChaCha chunk: 8 / gcd(8, K) steps consume whole blocks
+//   SDE_TT, SDE_UNR, SDE_CH        time tile, steps per unrolled group, ChaCha chunk (8 / gcd(8, K))
+//   SDE_NSLOT                      per-step model constants hoisted into the tile prologue
 //   sde_factor_is_wiener(k)        constexpr predicate
-//   sde_model_step(row, cache, ct, zu, u0, t_cur, t_next, dt, sqrt_dt)
+//   sde_model_step_consts(t_cur, t_next, dt, sqrt_dt, slots)     fills SDE_NSLOT doubles
+//   sde_model_step(row, cache, ct, zu, u0, ss)                   ss = {t_cur, t_next, dt, sqrt_dt, slots...}
 #pragma once
 #include "sde_device_rng.cuh"
 #include "sde_device_icdf.cuh"
@@ -36,9 +48,9 @@ struct SdeParams {
     const double* dts;        // [S]   times[t+1] - times[t]            (increment.rs:38-41)
     const double* sqrt_dts;   // [S]   sqrt(dts[t])                     (increment.rs:75-79)
     const double* x0;         // [P]   row 0                            (filtration.rs:42-50)
-    const sde_u32* sobol_V;     // [S*K][32] direction numbers, top 32 bits
-    const sde_u32* sobol_lane;  // [S*K][32] x_d(lane)
-    const sde_u64* xor_masks;   // [S*K]
+    const sde_u32* sobol_nib;   // [S*K][8][16]  XOR of direction numbers selected by nibble i of gray(n)
+    const sde_u32* sobol_lane;  // [S*K][32]     x_d(lane)
+    const sde_u32* xor_masks;   // [S*K]         32-bit digital-shift masks
     const double* inject;     // [N][S][K+1]
     double* out;
     double* partials;         // moments: [grid][P][3]
@@ -50,23 +62,31 @@ struct SdeParams {
 #ifndef SDE_KK
 #define SDE_KK (SDE_K > 0 ? SDE_K : 1)
 #endif
-// leading dimension of a warp's staging row: odd => conflict-free column writes
-#define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
-
-// shared-memory carve-up (bytes); mirrored by the host in lower.cpp
-//   icdf tables | output staging tile | per-tile step data {t, t+dt, dt, sqrt_dt} | Sobol: CTA/warp part,
-//   lane part and XOR masks of the tile's dimensions | moment scratch
-#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
-#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
-#define SDE_SMEM_STEP_BYTES (SDE_TT * 32)
-#define SDE_SMEM_MASK_BYTES ((SDE_RNG == 2) ? (SDE_TT * SDE_KK * 8) : 0)
-#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * SDE_NW * 4) : 0)
-#define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * 32 * 4) : 0)
-#define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_MASK_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES + SDE_SMEM_MOM_BYTES)
+#ifndef SDE_NSLOT
+#define SDE_NSLOT 0
+#endif
 #ifndef SDE_UNR
 #define SDE_UNR SDE_CH
 #endif
+// leading dimension of a warp's staging row: odd => conflict-free column writes
+#define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
+#define SDE_STEP_LD (4 + SDE_NSLOT)
+
+// shared-memory carve-up (bytes); mirrored by the host in lower.cpp
+//   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | moment scratch
+#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
+#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
+#define SDE_SMEM_STEP_BYTES (SDE_TT * SDE_STEP_LD * 8)
+#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * SDE_NW * 4) : 0)
+#define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * 32 * 4) : 0)
+#define SDE_SMEM_STAGE_BYTES (SDE_SMEM_STEP_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES)
+#define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + 2 * SDE_SMEM_STAGE_BYTES + SDE_SMEM_MOM_BYTES)
+
+// prefetch register counts (compile-time): entries of each staged table owned by one thread
+#define SDE_PF_BW ((SDE_TT * SDE_KK * SDE_NW + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_LANE ((SDE_TT * SDE_KK * 32 + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_STEP ((SDE_TT + SDE_BLOCK - 1) / SDE_BLOCK)
 
 struct SdeMoments { double n, mean, m2; };
 
@@ -91,17 +111,24 @@ __device__ __forceinline__ double sde_uniform_to_draw(double u, bool wiener, con
 #endif
 }
 
+// Registers that carry the next tile's staged data from the moment its loads are issued to the moment
+// they are written to shared memory (static indexing only).
+struct SdeTilePrefetch {
+    double st[SDE_PF_STEP][4];
+#if SDE_USES_SOBOL
+    sde_u32 bw[SDE_PF_BW];
+    sde_u32 ln[SDE_PF_LANE];
+#endif
+};
+
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
     extern __shared__ double4 sde_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
     double* s_icdf = reinterpret_cast<double*>(smem);
     double* s_tile = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES);
-    double* s_step = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES);
-    sde_u64* s_mask = reinterpret_cast<sde_u64*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES);
-    sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_MASK_BYTES);
-    sde_u32* s_lane = s_bw + (SDE_SMEM_BW_BYTES / 4);
+    unsigned char* s_stage = smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES;     // two buffers of SDE_SMEM_STAGE_BYTES
     double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_BYTES - SDE_SMEM_MOM_BYTES);
-    (void)s_icdf; (void)s_tile; (void)s_step; (void)s_mask; (void)s_bw; (void)s_lane; (void)s_mom;
+    (void)s_icdf; (void)s_tile; (void)s_mom;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -116,11 +143,86 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     const bool valid = (n >= first_n) && (n - first_n < prm.n_paths);
     const long long s_local = (long long)(n - first_n);           // may be "negative" for the <=5 leading pad threads
     const sde_u64 s_global = n - 5ull;
+    (void)s_global;
 
 #if SDE_ICDF == 1 && SDE_RNG != 4
     sde_icdf_table_load(s_icdf, tid, SDE_BLOCK);
-    __syncthreads();
 #endif
+
+    // ---- staging of one tile's read-only data (see header).  issue(): global loads into registers;
+    //      commit(): registers -> shared memory buffer `buf`.
+    auto issue = [&](const int t0, SdeTilePrefetch& pf) __attribute__((always_inline)) {
+        const int nt = min(SDE_TT, S - t0);
+#pragma unroll
+        for (int i = 0; i < SDE_PF_STEP; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < nt) {
+                pf.st[i][0] = __ldg(prm.times + t0 + e);
+                pf.st[i][1] = __ldg(prm.times + t0 + e + 1);
+                pf.st[i][2] = __ldg(prm.dts + t0 + e);
+                pf.st[i][3] = __ldg(prm.sqrt_dts + t0 + e);
+            }
+        }
+#if SDE_USES_SOBOL
+        const int nd = nt * SDE_K;
+        const size_t d0 = (size_t)t0 * SDE_K;
+#pragma unroll
+        for (int i = 0; i < SDE_PF_BW; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            sde_u32 x = 0;
+            if (e < nd * SDE_NW) {
+                // x_d(n_cta + 32 w) = XOR over the nibbles of gray(n) of a 16-entry table: 7 independent loads
+                const int dl = e / SDE_NW, w = e - dl * SDE_NW;
+                const sde_u32 nw = (sde_u32)n_cta + 32u * (sde_u32)w;
+                const sde_u32 g = nw ^ (nw >> 1);
+                const sde_u32* tab = prm.sobol_nib + (d0 + dl) * 128;
+#pragma unroll
+                for (int q = 1; q < 8; ++q) x ^= __ldg(tab + q * 16 + ((g >> (4 * q)) & 15u));
+#if SDE_RNG == 2
+                x ^= __ldg(prm.xor_masks + d0 + dl);      // fold the digital shift of this dimension in
+#endif
+            }
+            pf.bw[i] = x;
+        }
+#pragma unroll
+        for (int i = 0; i < SDE_PF_LANE; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            pf.ln[i] = (e < nd * 32) ? __ldg(prm.sobol_lane + d0 * 32 + e) : 0u;
+        }
+#endif
+    };
+    auto commit = [&](const int t0, const SdeTilePrefetch& pf, const int buf) __attribute__((always_inline)) {
+        const int nt = min(SDE_TT, S - t0);
+        double* st = reinterpret_cast<double*>(s_stage + buf * SDE_SMEM_STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < SDE_PF_STEP; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < nt) {
+                double* rec = st + e * SDE_STEP_LD;
+                rec[0] = pf.st[i][0]; rec[1] = pf.st[i][1]; rec[2] = pf.st[i][2]; rec[3] = pf.st[i][3];
+#if SDE_NSLOT > 0
+                double slots[SDE_NSLOT];
+                sde_model_step_consts(pf.st[i][0], pf.st[i][1], pf.st[i][2], pf.st[i][3], slots);
+#pragma unroll
+                for (int q = 0; q < SDE_NSLOT; ++q) rec[4 + q] = slots[q];
+#endif
+            }
+        }
+#if SDE_USES_SOBOL
+        sde_u32* bw = reinterpret_cast<sde_u32*>(s_stage + buf * SDE_SMEM_STAGE_BYTES + SDE_SMEM_STEP_BYTES);
+        sde_u32* ln = bw + SDE_SMEM_BW_BYTES / 4;
+#pragma unroll
+        for (int i = 0; i < SDE_PF_BW; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < SDE_TT * SDE_KK * SDE_NW) bw[e] = pf.bw[i];
+        }
+#pragma unroll
+        for (int i = 0; i < SDE_PF_LANE; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < SDE_TT * SDE_KK * 32) ln[e] = pf.ln[i];
+        }
+#endif
+    };
 
     // ScenarioFiltration::new — row 0 from initial_values, cache loaded from row 0 (filtration.rs:42-51)
     double row[SDE_P], cache[SDE_P];
@@ -148,36 +250,21 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     }
 #endif
 
-    for (int t0 = 0; t0 < S; t0 += SDE_TT) {
+    {   // tile 0 is staged synchronously
+        SdeTilePrefetch pf;
+        issue(0, pf);
+        commit(0, pf, 0);
+    }
+    __syncthreads();
+
+    int buf = 0;
+    for (int t0 = 0; t0 < S; t0 += SDE_TT, buf ^= 1) {
         const int t_end = min(t0 + SDE_TT, S);
-        // ---- tile prologue: everything the tile's steps read is staged in shared memory once per CTA
-        __syncthreads();
-        for (int e = tid; e < (t_end - t0); e += SDE_BLOCK) {
-            const int t = t0 + e;
-            s_step[4 * e + 0] = __ldg(prm.times + t);
-            s_step[4 * e + 1] = __ldg(prm.times + t + 1);
-            s_step[4 * e + 2] = __ldg(prm.dts + t);
-            s_step[4 * e + 3] = __ldg(prm.sqrt_dts + t);
-        }
-#if SDE_USES_SOBOL
-        {
-            const int nd = (t_end - t0) * SDE_K;
-            const size_t d0 = (size_t)t0 * SDE_K;
-            // x_d(n_cta + 32 w): the CTA/warp part of the point index, folded once per CTA
-            for (int e = tid; e < nd * SDE_NW; e += SDE_BLOCK) {
-                const int dl = e / SDE_NW, w = e - dl * SDE_NW;
-                s_bw[e] = sde_sobol_point32(prm.sobol_V + (d0 + dl) * 32, (sde_u32)n_cta + 32u * (sde_u32)w);
-            }
-            // x_d(lane): contiguous slice of the global lane table
-            for (int e = tid; e < nd * 32; e += SDE_BLOCK) s_lane[e] = __ldg(prm.sobol_lane + d0 * 32 + e);
-#if SDE_RNG == 2
-            for (int e = tid; e < nd; e += SDE_BLOCK) s_mask[e] = __ldg(prm.xor_masks + d0 + e);
-#endif
-        }
-#endif
-        __syncthreads();
-        // A group of SDE_UNR steps runs in two phases so that the scheduler sees SDE_UNR independent
-        // inverse-CDF chains side by side (they do not depend on the state) before the sequential state update:
+        const double* s_step = reinterpret_cast<const double*>(s_stage + buf * SDE_SMEM_STAGE_BYTES);
+        const sde_u32* s_bw = reinterpret_cast<const sde_u32*>(s_stage + buf * SDE_SMEM_STAGE_BYTES + SDE_SMEM_STEP_BYTES);
+        const sde_u32* s_lane = s_bw + SDE_SMEM_BW_BYTES / 4;
+        (void)s_bw; (void)s_lane;
+
         //   draw(t, j, ..)    uniforms -> normal / Poisson draws of step t (j = position in the group; it must be a
         //                     compile-time constant after unrolling so the ChaCha buffer is indexed statically)
         //   advance(t, ..)    one step of the scheme + staging of the new row
@@ -203,25 +290,31 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
 #if SDE_USES_SOBOL
                 const int dl = tl * SDE_K + k;
-                const sde_u32 x = s_bw[dl * SDE_NW + warp] ^ s_lane[dl * 32 + lane];
+                const sde_u32 x = s_bw[dl * SDE_NW + warp] ^ s_lane[dl * 32 + lane];    // (digitally shifted) Sobol integer
 #endif
-#if SDE_RNG == 0 || SDE_RNG == 2
-                // uniforms of the form j * 2^-53: stay in the integer pipe until the draw is needed
 #if SDE_RNG == 0
-                const sde_u64 j53 = jc;
-#else
-                // digital shift: one 64-bit mask per dimension; u = ((x ^ mask) >> 12 + 1/2) * 2^-52 = (2k+1) * 2^-53
-                const sde_u64 j53 = ((((((sde_u64)x) << 32) ^ s_mask[dl]) >> 12) << 1) | 1ull;
-#endif
-                if (k == 0 && SDE_NEEDS_U0) u0 = (double)(long long)j53 * 1.1102230246251565e-16;
+                // uniforms of the form j * 2^-53 stay in the integer pipe until the draw is needed
+                if (k == 0 && SDE_NEEDS_U0) u0 = (double)(long long)jc * 1.1102230246251565e-16;
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
-                    zu[k] = sde_icdf_normal_fast_j53(j53, s_icdf, lane);
+                    zu[k] = sde_icdf_normal_fast_j53(jc, s_icdf, lane);
 #else
-                    zu[k] = sde_icdf_normal_reference((double)(long long)j53 * 1.1102230246251565e-16);
+                    zu[k] = sde_icdf_normal_reference((double)(long long)jc * 1.1102230246251565e-16);
 #endif
                 } else {
-                    zu[k] = (double)(long long)j53 * 1.1102230246251565e-16;
+                    zu[k] = (double)(long long)jc * 1.1102230246251565e-16;
+                }
+#elif SDE_RNG == 2
+                // digital shift: u = ((x ^ mask) + 1/2) * 2^-32, one 32-bit mask per dimension (already folded into x)
+                if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+                if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1
+                    zu[k] = sde_icdf_normal_fast_k32(x, s_icdf, lane);
+#else
+                    zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
+#endif
+                } else {
+                    zu[k] = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
                 }
 #else
                 double u;
@@ -241,7 +334,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
         auto advance = [&](const int t, const double (&zu)[SDE_KK], const double u0) __attribute__((always_inline)) {
             const int tl = t - t0;
-            sde_model_step(row, cache, ct, zu, u0, s_step[4 * tl], s_step[4 * tl + 1], s_step[4 * tl + 2], s_step[4 * tl + 3]);
+            sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
 #if SDE_OUT == 0
 #pragma unroll
             for (int p = 0; p < SDE_P; ++p) my_tile[tl * SDE_P + p] = row[p];
@@ -253,16 +346,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #endif
         };
+        auto group = [&](const int tc) __attribute__((always_inline)) {
+            double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
+#pragma unroll
+            for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
+#pragma unroll
+            for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
+        };
+
+        const bool more = t0 + SDE_TT < S;                    // another tile follows: prefetch it behind the last group
+        SdeTilePrefetch pf;
         if (t_end - t0 == SDE_TT) {
-            // full tile: no guards inside the group
+            // full tile: no guards inside a group
 #pragma unroll 1
-            for (int tc = t0; tc < t0 + SDE_TT; tc += SDE_UNR) {
-                double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
-#pragma unroll
-                for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
-#pragma unroll
-                for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
-            }
+            for (int tc = t0; tc < t0 + SDE_TT - SDE_UNR; tc += SDE_UNR) group(tc);
+            if (more) issue(t0 + SDE_TT, pf);
+            group(t0 + SDE_TT - SDE_UNR);
         } else {
 #pragma unroll 1
             for (int tc = t0; tc < t_end; tc += SDE_UNR) {
@@ -276,20 +375,43 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 }
             }
         }
+        if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
+
 #if SDE_OUT == 0
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
         __syncwarp();
         {
             const double* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
             constexpr int NC = SDE_TT * SDE_P;                 // columns of a full tile
+            const size_t row_stride = (size_t)T * SDE_P;
             if (t_end - t0 == SDE_TT && valid_mask == 0xffffffffu) {
-                // full tile, all 32 paths live: flat index f -> (row r, column i) with compile-time NC
+                // full tile, all 32 paths live
                 double* dst0 = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P;
-                const size_t row_stride = (size_t)T * SDE_P;
-#pragma unroll 8
-                for (int f = lane; f < 32 * NC; f += 32) {
-                    const int r = f / NC, i = f - r * NC;
-                    dst0[(size_t)r * row_stride + i] = wt[r * SDE_TILE_LD + i];
+                if constexpr (NC <= 32 && 32 % NC == 0) {
+                    // a warp store covers 32/NC rows; running pointers, one 64-bit add per store
+                    constexpr int RPI = 32 / NC;
+                    const int r0 = lane / NC, i0 = lane % NC;
+                    double* p = dst0 + (size_t)r0 * row_stride + i0;
+                    const double* q = wt + r0 * SDE_TILE_LD + i0;
+#pragma unroll
+                    for (int it = 0; it < 32 / RPI; ++it) {
+                        *p = q[it * RPI * SDE_TILE_LD];
+                        p += RPI * row_stride;
+                    }
+                } else if constexpr (NC % 32 == 0) {
+                    double* p = dst0 + lane;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+#pragma unroll
+                        for (int c = 0; c < NC / 32; ++c) p[c * 32] = wt[r * SDE_TILE_LD + c * 32 + lane];
+                        p += row_stride;
+                    }
+                } else {
+#pragma unroll 4
+                    for (int f = lane; f < 32 * NC; f += 32) {
+                        const int r = f / NC, i = f - r * NC;
+                        dst0[(size_t)r * row_stride + i] = wt[r * SDE_TILE_LD + i];
+                    }
                 }
             } else {
                 const int ncols = (t_end - t0) * SDE_P;
@@ -303,6 +425,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         }
         __syncwarp();
 #endif
+        __syncthreads();                                      // next tile's staged data visible; this tile's buffer free
     }
 
 #if SDE_OUT == 2

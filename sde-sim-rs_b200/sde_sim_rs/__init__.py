@@ -75,7 +75,7 @@ class Universe:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and _ffi._lib is not None:
+        if h and _ffi is not None and getattr(_ffi, "_lib", None) is not None:     # may run at interpreter shutdown
             _ffi._lib.sde_universe_free(h)
 
 
@@ -132,7 +132,7 @@ class Plan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and _ffi._lib is not None:
+        if h and _ffi is not None and getattr(_ffi, "_lib", None) is not None:
             _ffi._lib.sde_plan_free(h)
 
     @property

@@ -80,12 +80,12 @@ def test_icdf_reference_mode_tolerance(oracle):
 
 
 def test_icdf_fast_mode_tolerance(oracle):
-    # Stated tolerance (device FAST vs oracle): |dz| <= 2e-13 absolute over p in [2^-53, 1 - 2^-53].
+    # Stated tolerance (device FAST vs oracle): |dz| <= 5e-13 absolute over p in [2^-53, 1 - 2^-53].
     p = _icdf_inputs()
     ref, got = oracle.icdf_normal(p), _icdf_dev(p, 1)
     err = np.abs(got - ref)
     print("fast icdf max abs err", err.max(), "at p =", p[np.argmax(err)])
-    assert err.max() <= 2e-13
+    assert err.max() <= 5e-13
 
 
 def test_icdf_zero_is_nan_both_modes():

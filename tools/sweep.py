@@ -22,7 +22,7 @@ out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
 for mode in which:
     for layout in ("NTP", "TPN"):
-        for tt, block in itertools.product((8, 16, 32), (128, 256)):
+        for tt, block in itertools.product((8, 16, 32), (128, 256, 512)):
             if layout == "TPN" and tt != 16:
                 continue
             try:

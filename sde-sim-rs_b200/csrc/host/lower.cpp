@@ -231,13 +231,22 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     int tt = opt.tile_steps;
     if (tt <= 0) {
         tt = 32;
-        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 16 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
+        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 32 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
         if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
     }
     // steps unrolled per loop trip: whole ChaCha blocks, and >= 4 for small models so that loads, constants and
     // the state-independent inverse-CDF chains of neighbouring steps overlap
     L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
     tt = std::max(L.unr, (tt / L.unr) * L.unr);
+    if (opt.tile_steps <= 0) {
+        // prefer a tile length that divides the step count (no partial last tile): search multiples of the
+        // unroll group in [tt/2, tt*9/8], nearest to the target first
+        const int S = u.T() - 1;
+        int best = 0;
+        for (int cand = L.unr; cand <= tt + tt / 8; cand += L.unr)
+            if (cand * 2 >= tt && S % cand == 0 && (best == 0 || std::abs(cand - tt) <= std::abs(best - tt))) best = cand;
+        if (best) tt = best;
+    }
     L.tt = tt;
     auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;

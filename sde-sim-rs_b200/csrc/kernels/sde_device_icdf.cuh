@@ -7,7 +7,7 @@
 //              operation order.  Differs from the CPU oracle only by CUDA's log (<= 1 ulp)
 //              vs glibc's: |dz| <= 4 ulp(z) away from p = 0.5, <= 1e-15 absolute near it.
 //   FAST       table-driven log (128 x {1/c, -2 ln c}, degree-4 log1p), rsqrt.approx.f64 +
-//              one Newton step, rcp.approx.f64 + one Newton step, FMA Horner: 18 FP64-pipe
+//              one cubic step, rcp.approx.f64 + one cubic step, FMA Horner: 21 FP64-pipe
 //              instructions instead of ~60.  Stated tolerance: |dz| <= 5e-13 absolute vs
 //              REFERENCE over p in [2^-53, 1 - 2^-53] (measured: tests/test_gpu_blocks.py).
 #pragma once
@@ -68,36 +68,46 @@ __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, in
     for (int h = tid; h < 64; h += nthreads) s_table[SDE_ICDF_LOG_DOUBLES + h] = (double)(h - 53) * -1.3862943611198906;
 }
 
-// Core: w = 1.mb * 2^(h-53) in (0, 0.5], given as mantissa bits mb (52 bits) and leading-one
-// position h of the 53-bit integer jw = w * 2^53.  Returns A&S x(w) (caller applies the sign).
-// 18 FP64-pipe instructions + 2 MUFU:
+// Constants of the FAST path live in constant memory so that FP64 instructions read them as
+// c[bank][offset] operands instead of spending issue slots on 64-bit immediate moves.
+__constant__ double sde_kc[12] = {
+    0x1.0000999a03338p-1,   // 0  a3  } degree-3 minimax polynomial for -2 log1p(r) / r on |r| <= 2^-8,
+    -0x1.55560888fbbc1p-1,  // 1  a2  } a1 = 1, a0 = -2 exact  (max |err| 4.9e-14 absolute in -2 ln w)
+    SDE_AS_C2, SDE_AS_C1, SDE_AS_C0,       // 2..4
+    SDE_AS_D3, SDE_AS_D2, SDE_AS_D1,       // 5..7
+    1.5, 0.0, 0.0, 0.0};
+
+// Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
+// byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
+// 21 FP64-pipe instructions + 2 MUFU:
 //   -2 ln w   table {1/c, -2 ln c} on the top 7 mantissa bits, r = m/c - 1 (|r| <= 2^-8), degree-3 minimax
-//             polynomial for -2 log1p(r)/r (|err| <= 4.9e-14 absolute in -2 ln w)                         6
-//   sqrt      rsqrt.approx.f64 seed (rel 2^-22.9) + one Newton step (rel <= 2.4e-14)                     3
-//   N/D       Horner with FMA (2 + 3), rcp.approx.f64 seed + one Newton step (rel <= 1.4e-14), t - q    9
+//             polynomial for -2 log1p(r)/r                                                               6
+//   sqrt      rsqrt.approx.f64 seed (it only sees the high word: rel ~2^-20) + one cubic step           5
+//   N/D       Horner with FMA (2 + 3), rcp.approx.f64 seed + one cubic step, t - q                      10
 // Stated tolerance of the whole map against the REFERENCE evaluation: |dz| <= 5e-13 absolute.
-__device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, int h, const double* s_table, int lane) {
-    const int idx = mb_hi >> 13;                             // top 7 of the 52 mantissa bits
+__device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, const double* eterm, const double* s_table_lane) {
     const double m = __hiloint2double((int)(mb_hi | 0x3ff00000u), (int)mb_lo);       // in [1, 2)
-    const double2 tc = *reinterpret_cast<const double2*>(s_table + 2 * (idx * SDE_ICDF_TABLE_REPL + (lane & (SDE_ICDF_TABLE_REPL - 1))));
+    // s_table_lane = s_table + (lane & 7) * 2: the copy of the log table this lane's bank group owns
+    const double2 tc = *reinterpret_cast<const double2*>(s_table_lane + (mb_hi >> 13) * (2 * SDE_ICDF_TABLE_REPL));
     const double r = fma(m, tc.x, -1.0);
-    double q = fma(r, 0x1.0000999a03338p-1, -0x1.55560888fbbc1p-1);
+    double q = fma(r, sde_kc[0], sde_kc[1]);
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
-    const double base = s_table[SDE_ICDF_LOG_DOUBLES + h] + tc.y;      // (h-53) * (-2 ln 2) - 2 ln c
+    const double base = *eterm + tc.y;                      // e * (-2 ln 2) - 2 ln c
     const double w2 = fma(q, r, base);                      // -2 ln w  in [1.386, 73.5]
-    // t = sqrt(w2): y0 ~ w2^-1/2; halve it in the integer pipe; t = g + g * (1 - g*y0)/2
+    // t = sqrt(w2): y0 ~ w2^-1/2, halved in the integer pipe; es = (1 - w2 y0^2)/2; t = g (1 + es + 1.5 es^2)
     const double y0 = sde_rsqrt_approx(w2);
     const double g = w2 * y0;
     const double yh = __hiloint2double(__double2hiint(y0) - 0x00100000, 0);          // y0 / 2 (low word of the seed is 0)
     const double es = fma(-g, yh, 0.5);
-    const double t = fma(g, es, g);
-    const double num = fma(fma(SDE_AS_C2, t, SDE_AS_C1), t, SDE_AS_C0);
-    const double den = fma(fma(fma(SDE_AS_D3, t, SDE_AS_D2), t, SDE_AS_D1), t, 1.0);
+    const double ps = fma(es, sde_kc[8], 1.0);
+    const double t = fma(g, es * ps, g);
+    const double num = fma(fma(sde_kc[2], t, sde_kc[3]), t, sde_kc[4]);
+    const double den = fma(fma(fma(sde_kc[5], t, sde_kc[6]), t, sde_kc[7]), t, 1.0);
     const double r0 = sde_rcp_approx(den);
     const double ed = fma(-den, r0, 1.0);
     const double q0 = num * r0;
-    const double quo = fma(q0, ed, q0);
+    const double quo = fma(q0, fma(ed, ed, ed), q0);
     return t - quo;
 }
 
@@ -108,7 +118,8 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
     const sde_u64 jw = upper ? (0x20000000000000ull - j) : j;   // exact 1 - p
     const int h = 63 - __clzll((long long)jw);               // jw in [1, 2^52]
     const sde_u64 mb = (jw << (52 - h)) & 0xfffffffffffffull;
-    double x = sde_icdf_as_core((sde_u32)(mb >> 32), (sde_u32)mb, h, s_table, lane);
+    double x = sde_icdf_as_core((sde_u32)(mb >> 32), (sde_u32)mb, s_table + SDE_ICDF_LOG_DOUBLES + h,
+                                s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
     int xhi = __double2hiint(x);
     xhi ^= upper ? 0 : 0x80000000;                           // p < 0.5 -> -x
     xhi = (j == 0) ? 0x7ff80000 : xhi;                       // ln(0) path of the reference -> NaN
@@ -120,11 +131,13 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
 __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const double* s_table, int lane) {
     const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
     const sde_u32 kw = k ^ (sde_u32)sgn;                     // top bit now clear; w = (2 kw + 1) * 2^-33
-    const int lz = __clz((int)kw);                           // 1..32 (32 when kw == 0: w = 2^-33 exactly)
-    // mantissa below the leading one of (kw:1), left aligned in 32 bits: shift in the centring bit, then zeros
-    sde_u32 mh = __funnelshift_lc(0x80000000u, kw, lz + 1);
+    const int pos = 31 - __clz((int)kw);                     // leading one of kw (-1 when kw == 0: w = 2^-33 exactly)
+    // mantissa below the leading one of (kw:1), left aligned in 32 bits: (kw : 0x80000000) >> pos, low word
+    sde_u32 mh = __funnelshift_r(0x80000000u, kw, pos);
     mh = (kw == 0u) ? 0u : mh;
-    double x = sde_icdf_as_core(mh >> 12, mh << 20, 52 - lz, s_table, lane);          // w = 1.m * 2^(-1-lz): h - 53 = -1 - lz
+    // w = 1.m * 2^(pos - 32): exponent term eln2[h], h - 53 = pos - 32
+    double x = sde_icdf_as_core(mh >> 12, mh << 20, s_table + SDE_ICDF_LOG_DOUBLES + 21 + pos,
+                                s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
     return __hiloint2double(xhi, __double2loint(x));
 }
@@ -135,7 +148,8 @@ __device__ __forceinline__ double sde_icdf_normal_fast(double p, const double* s
     const double w = lower ? p : 1.0 - p;                   // exact for every p the generators produce
     const int hi = __double2hiint(w);
     const int e = ((hi >> 20) & 0x7ff) - 1023;              // w = 1.m * 2^e, e in [-53, -1]
-    double x = sde_icdf_as_core((sde_u32)hi & 0x000fffffu, (sde_u32)__double2loint(w), min(max(e + 53, 0), 63), s_table, lane);
+    double x = sde_icdf_as_core((sde_u32)hi & 0x000fffffu, (sde_u32)__double2loint(w), s_table + SDE_ICDF_LOG_DOUBLES + min(max(e + 53, 0), 63),
+                                s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
     if (!(w > 0.0)) x = __longlong_as_double(0x7ff8000000000000ll);   // p = 0 -> NaN like ln(0) in the reference
     return lower ? -x : x;
 }

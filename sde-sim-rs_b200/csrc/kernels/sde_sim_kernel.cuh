@@ -356,22 +356,20 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 
         const bool more = t0 + SDE_TT < S;                    // another tile follows: prefetch it behind the last group
         SdeTilePrefetch pf;
-        if (t_end - t0 == SDE_TT) {
-            // full tile: no guards inside a group
+        {
+            // full groups run unguarded (any tile length); at most SDE_UNR - 1 trailing steps take the guarded path
+            const int n_groups = (t_end - t0) / SDE_UNR;
+            int tc = t0;
 #pragma unroll 1
-            for (int tc = t0; tc < t0 + SDE_TT - SDE_UNR; tc += SDE_UNR) group(tc);
+            for (int gi = 0; gi + 1 < n_groups; ++gi, tc += SDE_UNR) group(tc);
             if (more) issue(t0 + SDE_TT, pf);
-            group(t0 + SDE_TT - SDE_UNR);
-        } else {
-#pragma unroll 1
-            for (int tc = t0; tc < t_end; tc += SDE_UNR) {
+            if (n_groups > 0) { group(tc); tc += SDE_UNR; }
 #pragma unroll
-                for (int j = 0; j < SDE_UNR; ++j) {
-                    if (tc + j < t_end) {
-                        double zu[SDE_KK], u0;
-                        draw(tc + j, j, zu, u0);
-                        advance(tc + j, zu, u0);
-                    }
+            for (int j = 0; j < SDE_UNR - 1; ++j) {
+                if (tc + j < t_end) {
+                    double zu[SDE_KK], u0;
+                    draw(tc + j, j, zu, u0);
+                    advance(tc + j, zu, u0);
                 }
             }
         }
@@ -414,12 +412,17 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                     }
                 }
             } else {
+                // partial tile and/or dead lanes: one row at a time, running pointers
                 const int ncols = (t_end - t0) * SDE_P;
+                double* p = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P + lane;
+                const double* q = wt + lane;
+#pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     if ((valid_mask >> r) & 1u) {
-                        double* dst = prm.out + ((size_t)(s_warp0 + r) * T + (t0 + 1)) * SDE_P;
-                        for (int i = lane; i < ncols; i += 32) dst[i] = wt[r * SDE_TILE_LD + i];
+                        for (int i = lane; i < ncols; i += 32) p[i - lane] = q[i - lane];
                     }
+                    p += row_stride;
+                    q += SDE_TILE_LD;
                 }
             }
         }

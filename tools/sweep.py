@@ -22,8 +22,8 @@ out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
 for mode in which:
     for layout in ("NTP", "TPN"):
-        for tt, block in itertools.product((8, 16, 32), (128, 256, 512)):
-            if layout == "TPN" and tt != 16:
+        for tt, block in itertools.product((0, 28, 36), (128, 256)):
+            if layout == "TPN" and tt != 0:
                 continue
             try:
                 plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", layout=layout, tile_steps=tt,

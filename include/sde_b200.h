@@ -96,6 +96,8 @@ typedef struct sde_options {
                                  entry k<K is the normal z (Wiener factor) or uniform u (Poisson factor) of factor k, entry K is u[t][0] (RK's sk). */
     int32_t tile_steps;       /* 0 = auto; time-tile length override (tuning)                       */
     int32_t block_threads;    /* 0 = auto                                                           */
+    int32_t min_blocks;       /* 0 = auto; CTAs per SM promised to the compiler (tuning)            */
+    int32_t ntp_direct;       /* 0 = auto; 1 = force the shared-memory transpose for SDE_LAYOUT_NTP paths; 2 = force direct sector stores */
 } sde_options;
 
 void sde_options_default(sde_options* o);

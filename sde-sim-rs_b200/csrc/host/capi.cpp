@@ -73,6 +73,8 @@ PlanOptions plan_options(const Universe& u, const char* scheme, const char* rng_
     po.lower.rk_textbook = o.rk_variant == SDE_RK_TEXTBOOK;
     po.lower.block = o.block_threads;
     po.lower.tile_steps = o.tile_steps;
+    po.lower.min_blocks = o.min_blocks;
+    po.lower.direct = o.ntp_direct == 1 ? 0 : (o.ntp_direct == 2 ? 1 : -1);
     (void)u;
     return po;
 }

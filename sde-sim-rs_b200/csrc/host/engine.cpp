@@ -47,7 +47,7 @@ void joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit) {
         for (uint32_t i = 0; i < 18; ++i) minit[(size_t)d * 18 + i] = i < jk.stride ? jk.minit[(size_t)d * jk.stride + i] : 0;
 }
 
-void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib) {
+void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib, uint32_t lane_stride) {
     const JoeKuo& jk = joe_kuo();
     if (dims > jk.ndims) throw ExprError{"Sobol dimension " + std::to_string(dims) + " exceeds the Joe-Kuo table (21201)"};
     V.assign((size_t)dims * 32, 0);
@@ -71,8 +71,9 @@ void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>
         for (int i = 0; i < 32; ++i) Vd[i] = m[i] << (31 - i);   // top 32 bits of m_i << (63 - i)
         uint32_t* Ld = &lane[(size_t)d * 32];
         for (uint32_t l = 0; l < 32; ++l) {
-            uint32_t g = l ^ (l >> 1), x = 0;
-            for (int b = 0; b < 5; ++b) if ((g >> b) & 1u) x ^= Vd[b];
+            const uint32_t idx = l * lane_stride;
+            uint32_t g = idx ^ (idx >> 1), x = 0;
+            for (int b = 0; b < 32; ++b) if ((g >> b) & 1u) x ^= Vd[b];
             Ld[l] = x;
         }
         if (nib) {
@@ -157,7 +158,7 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
     d_x0_.alloc((size_t)u_.P() * 8);
     if (uses_sobol(opt_.lower.rng) && dims > 0) {
         std::vector<uint32_t> V, lane, nib;
-        sobol_tables((uint32_t)dims, V, lane, &nib);
+        sobol_tables((uint32_t)dims, V, lane, &nib, low_.direct ? 4u : 1u);
         d_nib_.upload(nib.data(), nib.size() * 4);
         d_lane_.upload(lane.data(), lane.size() * 4);
         if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 4);
@@ -232,6 +233,8 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
     const uint64_t first_n = scenario_offset + 5;            // Sobol::new(..).skip(5)  (sobol.rs:17)
     if (uses_sobol(opt_.lower.rng) && first_n + n > (1ull << 32))
         throw ExprError{"sobol point index exceeds 2^32 (the reference's scenario index is i32, src/sim/mod.rs:47)"};
+    if (low_.direct && ((uintptr_t)d_out & 31u))
+        throw ExprError{"full-path output buffer must be 32-byte aligned (256-bit sector stores)"};
     SdeParamsHost prm{};
     prm.n_paths = n;
     prm.scen_offset = scenario_offset;

@@ -17,7 +17,8 @@ void joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit /*[dims][18]*
 // V[d][b], b < 32: top 32 bits of the 64-bit direction numbers.  lane[d][l] = x_d(l), l < 32.
 // nib[d][i][v] (optional), i < 8, v < 16: XOR of V[d][4i+b] over the set bits b of v, so that
 // x_d(n) = XOR_i nib[d][i][(gray(n) >> 4i) & 15] — 8 independent loads instead of a bit loop.
-void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib = nullptr);
+void sobol_tables(uint32_t dims, std::vector<uint32_t>& V, std::vector<uint32_t>& lane, std::vector<uint32_t>* nib = nullptr,
+                  uint32_t lane_stride = 1);   // lane[d][l] = x_d(lane_stride * l)
 // u64 #i of ChaCha8Rng::seed_from_u64(seed) (host copy, used for the XOR digital-shift masks)
 void chacha8_u64_host(uint64_t seed, size_t n, uint64_t* out);
 

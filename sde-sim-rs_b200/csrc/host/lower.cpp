@@ -228,19 +228,23 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
 
     // ---- launch shape
     L.block = opt.block > 0 ? opt.block : 256;
-    int tt = opt.tile_steps;
-    if (tt <= 0) {
-        tt = 32;
-        if (opt.out == OUT_PATHS_NTP) tt = std::max(1, 32 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
-        if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
-    }
     // steps unrolled per loop trip: whole ChaCha blocks, and >= 4 for small models so that loads, constants and
     // the state-independent inverse-CDF chains of neighbouring steps overlap
     L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
+    // full paths in reference order: straight from registers as aligned 256-bit stores when a group is 4 steps
+    // and no ChaCha block alignment ties groups to the time origin; otherwise through the shared-memory transpose
+    L.direct = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && (L.block % 128) == 0 && P <= 8 && opt.direct != 0;
+    int tt = opt.tile_steps;
+    if (tt <= 0) {
+        tt = 32;
+        if (opt.out == OUT_PATHS_NTP && !L.direct) tt = std::max(1, 32 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
+        if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
+    }
     tt = std::max(L.unr, (tt / L.unr) * L.unr);
-    if (opt.tile_steps <= 0) {
+    if (opt.tile_steps <= 0 && (opt.out != OUT_PATHS_NTP || L.direct)) {
         // prefer a tile length that divides the step count (no partial last tile): search multiples of the
-        // unroll group in [tt/2, tt*9/8], nearest to the target first
+        // unroll group in [tt/2, tt*9/8], nearest to the target first.  The transposing NTP path keeps tt*P a
+        // divisor/multiple of 32 instead: that is what makes its flush cheap.
         const int S = u.T() - 1;
         int best = 0;
         for (int cand = L.unr; cand <= tt + tt / 8; cand += L.unr)
@@ -248,23 +252,25 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         if (best) tt = best;
     }
     L.tt = tt;
+    const int ts = tt + (L.direct ? 3 : 0);                  // SDE_TS
     auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
-        size_t tile = (opt.out == OUT_PATHS_NTP) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
-        size_t stage = (size_t)tt * (4 + nslot) * 8 + (sobol ? (size_t)tt * KK * nw * 4 + (size_t)tt * KK * 32 * 4 : 0);
+        size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
+        size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
         return icdf + tile + 2 * stage + mom;
     };
-    if (opt.block <= 0) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
+    if (opt.block <= 0 && !L.direct) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
     L.smem_bytes = smem_for(L.block);
     if (L.smem_bytes > 227 * 1024) throw ExprError{"model too large for the shared-memory staging tile (P = " + std::to_string(P) + ")"};
     {
-        const int regs_est = std::min(255, 56 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
+        const int regs_est = std::min(255, 56 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0) + 10 * (L.unr - 1));
         int by_regs = std::max(1, 65536 / (L.block * regs_est));
         int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / std::max<size_t>(L.smem_bytes, 1024));
         int by_threads = std::max(1, 2048 / L.block);
         L.min_blocks = std::max(1, std::min({by_regs, by_smem, by_threads}));
+        if (opt.min_blocks > 0) L.min_blocks = std::min(opt.min_blocks, std::min(by_smem, by_threads));
     }
 
     // ---- translation unit
@@ -282,7 +288,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
-    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n";
+    s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
     {

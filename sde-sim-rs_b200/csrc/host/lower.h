@@ -24,6 +24,8 @@ struct LowerOptions {
     bool rk_textbook = false;
     int block = 0;           // 0 = auto
     int tile_steps = 0;      // 0 = auto
+    int min_blocks = 0;      // 0 = auto: CTAs per SM promised to the compiler (__launch_bounds__)
+    int direct = -1;         // -1 = auto, 0/1 = force the shared-memory transpose / direct sector-store path for NTP paths
 };
 
 struct Lowered {
@@ -34,6 +36,7 @@ struct Lowered {
     int ch = 1;
     int unr = 1;             // steps unrolled per loop trip (multiple of ch)
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
+    bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
     bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)
 };
 

@@ -17,8 +17,16 @@
 //   and land in registers while it computes; one __syncthreads per tile.
 //   Inside a tile, groups of SDE_UNR steps run in two phases: first the state-independent uniform ->
 //   normal chains of the whole group (independent instruction streams for the scheduler), then the
-//   sequential state updates.  Full paths are transposed through a per-warp shared-memory tile so that
-//   each path's [t0+1, t0+TT] x P segment leaves as contiguous 8-byte-coalesced stores.
+//   sequential state updates.
+//   Full paths, reference row order [N][T][P], leave in one of two ways:
+//     SDE_DIRECT = 1  (Sobol / injected draws, groups of 4 steps): the lanes of a warp own paths that are 4 apart
+//       (path = cta + 128 (w>>2) + 4 lane + (w&3)), so all 32 rows start at the same offset modulo a 32-byte
+//       sector.  Each warp shifts its step groups by gamma in 0..3 steps so that a group's 4P values start
+//       on a sector boundary, and every lane writes them straight from registers as P aligned 256-bit stores
+//       (st.global.v4.f64): full sectors only, no shared-memory transpose, no flush.  The staged tables cover
+//       SDE_TT + 3 steps per tile to absorb the shift.
+//     SDE_DIRECT = 0  (ChaCha-driven modes, wide models): rows are transposed through a per-warp
+//       shared-memory tile and each path's [t0+1, t0+TT] x P segment leaves as contiguous 8-byte-coalesced stores.
 //
 // Macros expected from the generated prelude:
 //   SDE_P, SDE_K, SDE_KK           processes / stochastic factors / max(K, 1)
@@ -30,6 +38,7 @@
 //   SDE_BLOCK, SDE_MIN_BLOCKS      launch bounds
 //   SDE_TT, SDE_UNR, SDE_CH        time tile, steps per unrolled group, ChaCha chunk (8 / gcd(8, K))
 //   SDE_NSLOT                      per-step model constants hoisted into the tile prologue
+//   SDE_DIRECT                     1: register -> HBM sector stores for SDE_OUT == 0 (needs SDE_UNR == 4, no ChaCha)
 //   sde_factor_is_wiener(k)        constexpr predicate
 //   sde_model_step_consts(t_cur, t_next, dt, sqrt_dt, slots)     fills SDE_NSLOT doubles
 //   sde_model_step(row, cache, ct, zu, u0, ss)                   ss = {t_cur, t_next, dt, sqrt_dt, slots...}
@@ -68,6 +77,11 @@ struct SdeParams {
 #ifndef SDE_UNR
 #define SDE_UNR SDE_CH
 #endif
+#ifndef SDE_DIRECT
+#define SDE_DIRECT 0
+#endif
+// steps staged per tile buffer: the direct path lets a warp run up to 3 steps past the tile boundary
+#define SDE_TS (SDE_TT + (SDE_DIRECT ? 3 : 0))
 // leading dimension of a warp's staging row: odd => conflict-free column writes
 #define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
 #define SDE_STEP_LD (4 + SDE_NSLOT)
@@ -75,18 +89,18 @@ struct SdeParams {
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
 //   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | moment scratch
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
-#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
-#define SDE_SMEM_STEP_BYTES (SDE_TT * SDE_STEP_LD * 8)
-#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * SDE_NW * 4) : 0)
-#define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TT * SDE_KK * 32 * 4) : 0)
+#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0 && !SDE_DIRECT) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
+#define SDE_SMEM_STEP_BYTES (SDE_TS * SDE_STEP_LD * 8)
+#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * SDE_NW * 4) : 0)
+#define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * 32 * 4) : 0)
 #define SDE_SMEM_STAGE_BYTES (SDE_SMEM_STEP_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
 #define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + 2 * SDE_SMEM_STAGE_BYTES + SDE_SMEM_MOM_BYTES)
 
 // prefetch register counts (compile-time): entries of each staged table owned by one thread
-#define SDE_PF_BW ((SDE_TT * SDE_KK * SDE_NW + SDE_BLOCK - 1) / SDE_BLOCK)
-#define SDE_PF_LANE ((SDE_TT * SDE_KK * 32 + SDE_BLOCK - 1) / SDE_BLOCK)
-#define SDE_PF_STEP ((SDE_TT + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_BW ((SDE_TS * SDE_KK * SDE_NW + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_LANE ((SDE_TS * SDE_KK * 32 + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_STEP ((SDE_TS + SDE_BLOCK - 1) / SDE_BLOCK)
 
 struct SdeMoments { double n, mean, m2; };
 
@@ -138,7 +152,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 
     // thread -> point index n -> scenario (n - 5): the reference skips 5 points (sobol.rs:17)
     const sde_u64 n_cta = prm.n_base + (sde_u64)blockIdx.x * SDE_BLOCK;
+#if SDE_DIRECT
+    // lanes own paths 4 apart so that every row of a warp has the same phase modulo a 32-byte sector
+    const sde_u64 n = n_cta + (sde_u64)(128 * (warp >> 2) + 4 * lane + (warp & 3));
+#else
     const sde_u64 n = n_cta + (sde_u64)tid;
+#endif
     const sde_u64 first_n = prm.scen_offset + 5ull;
     const bool valid = (n >= first_n) && (n - first_n < prm.n_paths);
     const long long s_local = (long long)(n - first_n);           // may be "negative" for the <=5 leading pad threads
@@ -152,7 +171,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     // ---- staging of one tile's read-only data (see header).  issue(): global loads into registers;
     //      commit(): registers -> shared memory buffer `buf`.
     auto issue = [&](const int t0, SdeTilePrefetch& pf) __attribute__((always_inline)) {
-        const int nt = min(SDE_TT, S - t0);
+        const int nt = min(SDE_TS, S - t0);
 #pragma unroll
         for (int i = 0; i < SDE_PF_STEP; ++i) {
             const int e = tid + i * SDE_BLOCK;
@@ -173,11 +192,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             if (e < nd * SDE_NW) {
                 // x_d(n_cta + 32 w) = XOR over the nibbles of gray(n) of a 16-entry table: 7 independent loads
                 const int dl = e / SDE_NW, w = e - dl * SDE_NW;
+#if SDE_DIRECT
+                const sde_u32 nw = (sde_u32)n_cta + 128u * (sde_u32)(w >> 2) + (sde_u32)(w & 3);
+#else
                 const sde_u32 nw = (sde_u32)n_cta + 32u * (sde_u32)w;
+#endif
                 const sde_u32 g = nw ^ (nw >> 1);
                 const sde_u32* tab = prm.sobol_nib + (d0 + dl) * 128;
 #pragma unroll
-                for (int q = 1; q < 8; ++q) x ^= __ldg(tab + q * 16 + ((g >> (4 * q)) & 15u));
+                for (int q = (SDE_DIRECT ? 0 : 1); q < 8; ++q) x ^= __ldg(tab + q * 16 + ((g >> (4 * q)) & 15u));
 #if SDE_RNG == 2
                 x ^= __ldg(prm.xor_masks + d0 + dl);      // fold the digital shift of this dimension in
 #endif
@@ -192,7 +215,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
     };
     auto commit = [&](const int t0, const SdeTilePrefetch& pf, const int buf) __attribute__((always_inline)) {
-        const int nt = min(SDE_TT, S - t0);
+        const int nt = min(SDE_TS, S - t0);
         double* st = reinterpret_cast<double*>(s_stage + buf * SDE_SMEM_STAGE_BYTES);
 #pragma unroll
         for (int i = 0; i < SDE_PF_STEP; ++i) {
@@ -214,12 +237,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
         for (int i = 0; i < SDE_PF_BW; ++i) {
             const int e = tid + i * SDE_BLOCK;
-            if (e < SDE_TT * SDE_KK * SDE_NW) bw[e] = pf.bw[i];
+            if (e < SDE_TS * SDE_KK * SDE_NW) bw[e] = pf.bw[i];
         }
 #pragma unroll
         for (int i = 0; i < SDE_PF_LANE; ++i) {
             const int e = tid + i * SDE_BLOCK;
-            if (e < SDE_TT * SDE_KK * 32) ln[e] = pf.ln[i];
+            if (e < SDE_TS * SDE_KK * 32) ln[e] = pf.ln[i];
         }
 #endif
     };
@@ -240,9 +263,16 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
         for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)s_local * T * SDE_P + p] = row[p];
     }
+#if SDE_DIRECT
+    double* const my_row = prm.out + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's row [T][P]
+    // step shift of this warp: the group that starts at step gamma writes elements from (gamma+1) P on, and
+    // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
+    const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
+#else
     double* my_tile = s_tile + (size_t)(warp * 32 + lane) * SDE_TILE_LD;
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
     const long long s_warp0 = s_local - lane;
+#endif
 #elif SDE_OUT == 1
     if (valid) {
 #pragma unroll
@@ -335,7 +365,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         auto advance = [&](const int t, const double (&zu)[SDE_KK], const double u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
-#if SDE_OUT == 0
+#if SDE_OUT == 0 && !SDE_DIRECT
 #pragma unroll
             for (int p = 0; p < SDE_P; ++p) my_tile[tl * SDE_P + p] = row[p];
 #elif SDE_OUT == 1
@@ -350,12 +380,64 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
+#if SDE_DIRECT
+            double vals[SDE_UNR * SDE_P];                     // rows tc+1 .. tc+4, in output order
+#pragma unroll
+            for (int j = 0; j < SDE_UNR; ++j) {
+                advance(tc + j, zu[j], u0[j]);
+#pragma unroll
+                for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
+            }
+            if (valid) {
+                double* dst = my_row + (size_t)(tc + 1) * SDE_P;      // 32-byte aligned by the choice of gamma
+#pragma unroll
+                for (int q = 0; q < SDE_P; ++q)
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]),
+                                 "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+            }
+#else
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
+#endif
+        };
+        // one step on its own (ragged ends); direct mode stores its row element-wise
+        auto single = [&](const int t, const int j) __attribute__((always_inline)) {
+            double zu[SDE_KK], u0;
+            draw(t, j, zu, u0);
+            advance(t, zu, u0);
+#if SDE_DIRECT
+            if (valid) {
+#pragma unroll
+                for (int p = 0; p < SDE_P; ++p) my_row[(size_t)(t + 1) * SDE_P + p] = row[p];
+            }
+#endif
         };
 
         const bool more = t0 + SDE_TT < S;                    // another tile follows: prefetch it behind the last group
         SdeTilePrefetch pf;
+#if SDE_DIRECT
+        {
+            // this warp's steps in tile k: [t0 + gamma, t0 + TT + gamma), clipped to the last full group; the first
+            // gamma steps of the path and the <= 3 steps after the last full group run on their own
+            const int g_eff = min(gamma, S);
+            const int s_full = g_eff + ((S - g_eff) & ~3);
+            if (t0 == 0) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (j < g_eff) single(j, j);
+            }
+            int tc = t0 + g_eff;
+            const int t_hi = min(t0 + SDE_TT + g_eff, s_full);
+            const int n_groups = t_hi > tc ? (t_hi - tc) >> 2 : 0;
+#pragma unroll 1
+            for (int gi = 0; gi + 1 < n_groups; ++gi, tc += 4) group(tc);
+            if (more) issue(t0 + SDE_TT, pf);
+            if (n_groups > 0) { group(tc); tc += 4; }
+            if (!more) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (s_full + j < S) single(s_full + j, j);
+            }
+        }
+#else
         {
             // full groups run unguarded (any tile length); at most SDE_UNR - 1 trailing steps take the guarded path
             const int n_groups = (t_end - t0) / SDE_UNR;
@@ -365,24 +447,21 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             if (more) issue(t0 + SDE_TT, pf);
             if (n_groups > 0) { group(tc); tc += SDE_UNR; }
 #pragma unroll
-            for (int j = 0; j < SDE_UNR - 1; ++j) {
-                if (tc + j < t_end) {
-                    double zu[SDE_KK], u0;
-                    draw(tc + j, j, zu, u0);
-                    advance(tc + j, zu, u0);
-                }
-            }
+            for (int j = 0; j < SDE_UNR - 1; ++j)
+                if (tc + j < t_end) single(tc + j, j);
         }
+#endif
         if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
 
-#if SDE_OUT == 0
+#if SDE_OUT == 0 && !SDE_DIRECT
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
         __syncwarp();
         {
             const double* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
             constexpr int NC = SDE_TT * SDE_P;                 // columns of a full tile
             const size_t row_stride = (size_t)T * SDE_P;
-            if (t_end - t0 == SDE_TT && valid_mask == 0xffffffffu) {
+            constexpr bool kRegularNC = (NC <= 32 && 32 % NC == 0) || (NC % 32 == 0);
+            if (kRegularNC && t_end - t0 == SDE_TT && valid_mask == 0xffffffffu) {
                 // full tile, all 32 paths live
                 double* dst0 = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P;
                 if constexpr (NC <= 32 && 32 % NC == 0) {
@@ -396,19 +475,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                         *p = q[it * RPI * SDE_TILE_LD];
                         p += RPI * row_stride;
                     }
-                } else if constexpr (NC % 32 == 0) {
+                } else {
                     double* p = dst0 + lane;
 #pragma unroll 4
                     for (int r = 0; r < 32; ++r) {
 #pragma unroll
                         for (int c = 0; c < NC / 32; ++c) p[c * 32] = wt[r * SDE_TILE_LD + c * 32 + lane];
                         p += row_stride;
-                    }
-                } else {
-#pragma unroll 4
-                    for (int f = lane; f < 32 * NC; f += 32) {
-                        const int r = f / NC, i = f - r * NC;
-                        dst0[(size_t)r * row_stride + i] = wt[r * SDE_TILE_LD + i];
                     }
                 }
             } else {

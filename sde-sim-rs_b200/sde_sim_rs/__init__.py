@@ -85,7 +85,8 @@ def parse_equations(processes_equations: Sequence[str], time_steps: Sequence[flo
 
 
 def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, layout: str, scramble: str, icdf: str,
-                  arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0):
+                  arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0,
+                  min_blocks: int = 0, ntp_direct: int = 0):
     o = _ffi.default_options()
     o.device = device
     o.seed = seed & (2**64 - 1)
@@ -99,6 +100,8 @@ def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, 
     o.inject = inject_ptr or None
     o.tile_steps = tile_steps
     o.block_threads = block_threads
+    o.min_blocks = min_blocks
+    o.ntp_direct = ntp_direct
     return o
 
 
@@ -114,7 +117,7 @@ class Plan:
     def __init__(self, universe: Universe, scheme: str = "euler", rng_method: str = "pseudo", *, output: str = "paths",
                  layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
                  arithmetic: str = "strict", rk_variant: str = "reference", device: Optional[int] = None,
-                 inject=None, tile_steps: int = 0, block_threads: int = 0):
+                 inject=None, tile_steps: int = 0, block_threads: int = 0, min_blocks: int = 0, ntp_direct: int = 0):
         self.universe = universe
         self.scheme, self.rng_method = scheme, rng_method
         self.output, self.layout = output, layout
@@ -123,7 +126,7 @@ class Plan:
         opts = _make_options(device=self.device, seed=0, scenario_offset=0, output=output, layout=layout,
                              scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant,
                              inject_ptr=(inject.data_ptr() if inject is not None else 0), tile_steps=tile_steps,
-                             block_threads=block_threads)
+                             block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct)
         h = C.c_void_p()
         rc = _ffi.lib().sde_plan_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), C.byref(h))
         _ffi.check(rc, prefix_runtime="Simulation failed: ")

@@ -39,6 +39,8 @@ class SdeOptions(C.Structure):
         ("inject", C.c_void_p),
         ("tile_steps", C.c_int32),
         ("block_threads", C.c_int32),
+        ("min_blocks", C.c_int32),
+        ("ntp_direct", C.c_int32),
     ]
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Tuning sweep on a GPU box: time the fused kernel on the C2 workload (reduced N) for a grid of
-(tile_steps, block_threads) and print path-steps/s; used to pick the lowering defaults."""
+"""Tuning sweep on a GPU box: time the fused kernel on the C2 workload (reduced N) over launch-shape options
+and print path-steps/s; used to pick the lowering defaults."""
 import itertools
 import json
 import os
@@ -20,30 +20,31 @@ modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="refe
 which = sys.argv[1:] or ["fast"]
 out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
+grid = [("NTP", d, tt, b, mb) for d in (2, 1) for tt in (0, 28, 64) for b in (128, 256) for mb in (2, 3, 4)]
+grid += [("TPN", 0, 0, 256, mb) for mb in (2, 3, 4)]
 for mode in which:
-    for layout in ("NTP", "TPN"):
-        for tt, block in itertools.product((0, 28, 36), (128, 256)):
-            if layout == "TPN" and tt != 0:
-                continue
-            try:
-                plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", layout=layout, tile_steps=tt,
-                              block_threads=block, **modes[mode])
-                o = out if layout == "NTP" else out.view(D + 1, 1, N)
-                for _ in range(2):
-                    plan.run({"X1": 1.0}, N, seed=42, out=o)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    plan.run({"X1": 1.0}, N, seed=42, out=o)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 5
-                r = {"mode": mode, "layout": layout, "tt": tt, "block": block, "ms": ms, "gps": N * D / ms / 1e6,
-                     "gbs": N * (D + 1) * 8 / ms / 1e6}
-            except Exception as ex:  # noqa: BLE001
-                r = {"mode": mode, "layout": layout, "tt": tt, "block": block, "error": str(ex)[:200]}
-            print(json.dumps(r), flush=True)
-            res.append(r)
+    for layout, direct, tt, block, mb in grid:
+        if direct == 1 and (tt == 64 or mb != 2):
+            continue
+        try:
+            plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", layout=layout, tile_steps=tt,
+                          block_threads=block, min_blocks=mb, ntp_direct=direct, **modes[mode])
+            o = out if layout == "NTP" else out.view(D + 1, 1, N)
+            for _ in range(2):
+                plan.run({"X1": 1.0}, N, seed=42, out=o)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                plan.run({"X1": 1.0}, N, seed=42, out=o)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            r = {"mode": mode, "layout": layout, "direct": direct, "tt": tt, "block": block, "min_blocks": mb, "ms": round(ms, 4),
+                 "gps": round(N * D / ms / 1e6, 1), "gbs": round(N * (D + 1) * 8 / ms / 1e6, 1)}
+        except Exception as ex:  # noqa: BLE001
+            r = {"mode": mode, "layout": layout, "direct": direct, "tt": tt, "block": block, "min_blocks": mb, "error": str(ex)[:200]}
+        print(json.dumps(r), flush=True)
+        res.append(r)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)

@@ -72,6 +72,7 @@ DriverState& driver_state() {
 
 struct NvrtcState {
     NvrtcApi api{};
+    int major = 0, minor = 0;
     bool ok = false;
     std::string why;
 };
@@ -80,7 +81,12 @@ NvrtcState& nvrtc_state() {
     static NvrtcState st;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", nullptr};
+        // Prefer the toolkit's NVRTC by path: a process that imported PyTorch already holds torch's bundled
+        // libnvrtc.so.12 (CUDA 12.8), which a bare soname lookup would return and whose ptxas predates
+        // 256-bit vector stores.
+        std::string cuda_home = std::getenv("CUDA_HOME") ? std::getenv("CUDA_HOME") : "/usr/local/cuda";
+        std::string p1 = cuda_home + "/lib64/libnvrtc.so.12", p2 = cuda_home + "/targets/x86_64-linux/lib/libnvrtc.so.12";
+        const char* names[] = {p1.c_str(), p2.c_str(), "libnvrtc.so.12", "libnvrtc.so", nullptr};
         std::string tried;
         void* h = open_first(names, &tried);
         if (!h) { st.why = "NVRTC not found (tried " + tried + ")"; return; }
@@ -90,9 +96,10 @@ NvrtcState& nvrtc_state() {
         if (!st.api.field) missing = true;
         SDE_LOAD(nvrtcCreateProgram) SDE_LOAD(nvrtcDestroyProgram) SDE_LOAD(nvrtcCompileProgram)
         SDE_LOAD(nvrtcGetCUBINSize) SDE_LOAD(nvrtcGetCUBIN) SDE_LOAD(nvrtcGetProgramLogSize)
-        SDE_LOAD(nvrtcGetProgramLog) SDE_LOAD(nvrtcGetErrorString)
+        SDE_LOAD(nvrtcGetProgramLog) SDE_LOAD(nvrtcGetErrorString) SDE_LOAD(nvrtcVersion)
 #undef SDE_LOAD
         if (missing) { st.why = "NVRTC is missing symbols"; return; }
+        st.api.nvrtcVersion(&st.major, &st.minor);
         st.ok = true;
     });
     return st;
@@ -170,8 +177,11 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
     nvrtcProgram prog;
     nvrtcResult r = n.nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), (int)names.size(), ptrs.data(), names.data());
     if (r != NVRTC_SUCCESS) throw CudaError{std::string("nvrtcCreateProgram: ") + n.nvrtcGetErrorString(r)};
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
-    r = n.nvrtcCompileProgram(prog, 3, opts);
+    // st.global.v4.f64 (256-bit) needs the CUDA 12.9 ptxas; older NVRTC falls back to two 128-bit stores
+    NvrtcState& nst = nvrtc_state();
+    const bool st256 = nst.major > 12 || (nst.major == 12 && nst.minor >= 9);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", st256 ? "-DSDE_ST256=1" : "-DSDE_ST256=0"};
+    r = n.nvrtcCompileProgram(prog, 4, opts);
     size_t ls = 0;
     n.nvrtcGetProgramLogSize(prog, &ls);
     std::string lg(ls, '\0');

@@ -62,6 +62,7 @@ struct NvrtcApi {
     nvrtcResult (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*);
     nvrtcResult (*nvrtcGetProgramLog)(nvrtcProgram, char*);
     const char* (*nvrtcGetErrorString)(nvrtcResult);
+    nvrtcResult (*nvrtcVersion)(int*, int*);
 };
 
 // Throws CudaError when the library cannot be loaded.

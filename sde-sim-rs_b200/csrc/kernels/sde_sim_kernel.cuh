@@ -80,6 +80,9 @@ struct SdeParams {
 #ifndef SDE_DIRECT
 #define SDE_DIRECT 0
 #endif
+#ifndef SDE_ST256
+#define SDE_ST256 1   /* 256-bit st.global.v4.f64 (PTX ISA 8.8 / CUDA 12.9 ptxas) */
+#endif
 // steps staged per tile buffer: the direct path lets a warp run up to 3 steps past the tile boundary
 #define SDE_TS (SDE_TT + (SDE_DIRECT ? 3 : 0))
 // leading dimension of a warp's staging row: odd => conflict-free column writes
@@ -391,9 +394,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             if (valid) {
                 double* dst = my_row + (size_t)(tc + 1) * SDE_P;      // 32-byte aligned by the choice of gamma
 #pragma unroll
-                for (int q = 0; q < SDE_P; ++q)
+                for (int q = 0; q < SDE_P; ++q) {
+#if SDE_ST256
                     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]),
                                  "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+#else
+                    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]) : "memory");
+                    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + 4 * q + 2), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+#endif
+                }
             }
 #else
 #pragma unroll

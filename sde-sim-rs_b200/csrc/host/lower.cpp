@@ -265,7 +265,8 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     L.smem_bytes = smem_for(L.block);
     if (L.smem_bytes > 227 * 1024) throw ExprError{"model too large for the shared-memory staging tile (P = " + std::to_string(P) + ")"};
     {
-        const int regs_est = std::min(255, 56 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0) + 10 * (L.unr - 1));
+        // measured on B200 (tools/sweep.py): 4 CTAs x 256 threads at a 64-register cap beat 2-3 CTAs with more registers
+        const int regs_est = std::min(255, 52 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
         int by_regs = std::max(1, 65536 / (L.block * regs_est));
         int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / std::max<size_t>(L.smem_bytes, 1024));
         int by_threads = std::max(1, 2048 / L.block);

@@ -22,12 +22,29 @@ class StepGen {
     // path-independent per-step constants hoisted into the tile prologue (arithmetic=fast only):
     // each entry is a CUDA expression over t_cur, t_next, dt, sqrt_dt
     std::vector<std::string> slots;
+    std::string prelude() const { return pre_.str(); }      // declarations emitted before the step body
 
     // Emits the body of sde_model_step given the cache position on entry; returns it on exit.
     CacheAt generate(CacheAt enter, std::ostringstream& o) {
         state_ = enter;
         o_ = &o;
         slots.clear();
+        pre_.str("");
+        w_declared_.assign(u_.K(), false);
+        {   // hoist per-step constants into the tile prologue only while the step record stays small
+            size_t n = 0;
+            double lin[128];
+            if (!opt_.strict && opt_.scheme == SCHEME_EULER)
+                for (int p : u_.levy_indices) {
+                    const Process& pr = u_.processes[p];
+                    if (!linear_in_own_state(pr, p, lin)) continue;
+                    std::vector<bool> used(u_.K(), false);
+                    for (const Term& t : pr.terms) if (t.kind == IncKind::Wiener) used[t.factor] = true;
+                    n += 1;
+                    for (bool b : used) n += b ? 1 : 0;
+                }
+            hoist_ = n <= 16;
+        }
         const int P = u_.P();
         for (int p = 0; p < P; ++p) line("double n" + std::to_string(p) + " = 0.0;");   // row t+1 is zero until set (filtration.rs:28)
         if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
@@ -40,6 +57,9 @@ class StepGen {
     const LowerOptions& opt_;
     CacheAt state_ = OLD;
     std::ostringstream* o_ = nullptr;
+    std::ostringstream pre_;
+    std::vector<bool> w_declared_;
+    bool hoist_ = true;
 
     void line(const std::string& s) { *o_ << "    " << s << "\n"; }
     std::string mul(const std::string& a, const std::string& b) const { return opt_.strict ? "__dmul_rn(" + a + ", " + b + ")" : "(" + a + " * " + b + ")"; }
@@ -110,12 +130,23 @@ class StepGen {
                     if (t.kind == IncKind::Time) A = "fma(" + format_double(lin[j]) + ", dt, " + A + ")";
                     else if (t.kind == IncKind::Wiener) { bsum[t.factor] += lin[j]; bused[t.factor] = true; }
                 }
-                slots.push_back(A);
-                line("double g = ss[" + std::to_string(3 + slots.size()) + "];");
-                for (int k = 0; k < u_.K(); ++k) {
-                    if (!bused[k]) continue;
-                    slots.push_back("(" + format_double(bsum[k]) + " * sqrt_dt)");
-                    line("g = fma(ss[" + std::to_string(3 + slots.size()) + "], zu[" + std::to_string(k) + "], g);");
+                if (hoist_) {
+                    slots.push_back(A);
+                    line("double g = ss[" + std::to_string(3 + slots.size()) + "];");
+                    for (int k = 0; k < u_.K(); ++k) {
+                        if (!bused[k]) continue;
+                        slots.push_back("(" + format_double(bsum[k]) + " * sqrt_dt)");
+                        line("g = fma(ss[" + std::to_string(3 + slots.size()) + "], zu[" + std::to_string(k) + "], g);");
+                    }
+                } else {
+                    // many (process, factor) pairs (e.g. a Cholesky-loaded basket): loadings stay immediates and the
+                    // scaled draws w_k = sqrt(dt) z_k are shared by all processes
+                    line("double g = " + A + ";");
+                    for (int k = 0; k < u_.K(); ++k) {
+                        if (!bused[k]) continue;
+                        if (!w_declared_[k]) { pre_ << "    const double w" << k << " = sqrt_dt * zu[" << k << "];\n"; w_declared_[k] = true; }
+                        line("g = fma(" + format_double(bsum[k]) + ", w" + std::to_string(k) + ", g);");
+                    }
                 }
                 for (size_t j = 0; j < pr.terms.size(); ++j) {
                     if (pr.terms[j].kind != IncKind::Poisson) continue;
@@ -309,7 +340,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
          "                                               const double u0, const double* __restrict__ ss) {\n";
     s << "    const double t_cur = ss[0], t_next = ss[1], dt = ss[2], sqrt_dt = ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
-    s << body.str();
+    s << gen.prelude() << body.str();
     s << "}\n#include \"sde_sim_kernel.cuh\"\n";
     L.source = s.str();
     return L;

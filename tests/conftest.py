@@ -33,3 +33,20 @@ HESTON_EQ = [
 def grid(D, S=None):
     S = D if S is None else S
     return [k / D for k in range(S + 1)]
+
+
+def basket_equations(n_assets=64, rho=0.5):
+    """C4: correlated GBM basket written the way the reference expresses correlation —
+    shared dW names with explicit Cholesky loadings (src/proc/util.rs:145-146)."""
+    import numpy as np
+
+    corr = np.full((n_assets, n_assets), rho)
+    np.fill_diagonal(corr, 1.0)
+    L = np.linalg.cholesky(corr)
+    eqs = []
+    for i in range(n_assets):
+        sig = 0.1 + 0.2 * i / max(n_assets - 1, 1)
+        terms = [f"( 0.05 * S{i} ) * dt"] + [f"( {sig * L[i, j]:.17g} * S{i} ) * dW{j + 1}" for j in range(i + 1)]
+        eqs.append(f"dS{i} = " + " + ".join(terms))
+    init = {f"S{i}": 100.0 for i in range(n_assets)}
+    return eqs, init

@@ -176,3 +176,92 @@ def test_run_host_matches_device_run():
     pinned = torch.empty((N, 51, 1), dtype=torch.float64).pin_memory()
     plan.run_host(init, N, seed=4, out=pinned)
     assert np.array_equal(pinned.numpy(), dev)
+
+
+# ---------------------------------------------------------------- remaining BASELINE configs + store paths
+def test_direct_and_transposed_store_paths_are_bit_identical():
+    # full-path [N][T][P] output has two implementations: 256-bit sector stores straight from
+    # registers vs the shared-memory transpose; same arithmetic, so the bytes must agree
+    for eqs, times, init, N in [(GBM_EQ, grid(252), {"X1": 1.0}, 5003), (HESTON_EQ, grid(1000, 123), {"S": 100.0, "v": 0.04}, 2050)]:
+        outs = []
+        for direct in (1, 2):
+            plan = S.Plan(S.Universe(eqs, times), "euler", "sobol", scramble="xor", ntp_direct=direct)
+            outs.append(plan.run(init, N, seed=11, scenario_offset=77).cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])
+
+
+def test_direct_store_needs_aligned_output():
+    plan = S.Plan(S.Universe(GBM_EQ, grid(252, 8)), "euler", "sobol", scramble="xor")
+    buf = torch.empty(100 * 9 + 1, dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError, match="32-byte aligned"):
+        plan.run({"X1": 1.0}, 100, out=buf[1:].view(100, 9, 1))
+
+
+@pytest.mark.parametrize("eqs,times,init,N,wiener,scheme", [
+    (GBM_EQ, grid(252), {"X1": 1.0}, 1024, [True], "euler"),
+    (HESTON_EQ, grid(1000, 300), {"S": 100.0, "v": 0.04}, 256, [True, True], "runge-kutta"),
+])
+def test_fast_arithmetic_identical_draws_within_1e12(oracle, eqs, times, init, N, wiener, scheme):
+    # arithmetic="fast" (FMA contraction + multiplicative rewrite of a_j*X coefficients): identical normal draws
+    # must still reproduce the oracle's strictly ordered f64 arithmetic to 1e-12 relative
+    U = oracle.Universe(eqs, times)
+    inj = _inject(oracle, U, N, "pseudo", 5, wiener)
+    ref = oracle.simulate(U, init, N, scheme, inject=inj)
+    plan = S.Plan(S.Universe(eqs, times), scheme, "pseudo", inject=torch.from_numpy(inj).cuda(), arithmetic="fast")
+    got = plan.run(init, N).cpu().numpy()
+    assert rel_err(got, ref) <= 1e-12, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("arithmetic,icdf,tol", [("strict", "reference", 1e-12), ("fast", "fast", 1e-12)])
+def test_c4_basket_64_factors_matches_oracle(oracle, arithmetic, icdf, tol):
+    # C4: 64-dim correlated GBM basket, Sobol dims = 64 x 252 = 16128, correlation through shared dW names
+    from conftest import basket_equations
+
+    eqs, init = basket_equations(64)
+    times, N = grid(252), 96
+    U = oracle.Universe(eqs, times)
+    assert (U.P, U.K) == (64, 64) and U.factors[:3] == ["dW1", "dW2", "dW3"]
+    ref = oracle.simulate(U, init, N, "euler", "sobol", seed=3, scramble="xor")
+    got = S.simulate(eqs, times, N, init, "sobol", "euler", seed=3, scramble="xor", arithmetic=arithmetic, icdf=icdf).to_numpy()
+    assert rel_err(got, ref) <= tol, rel_err(got, ref)
+    mom = S.simulate(eqs, times, N, init, "sobol", "euler", seed=3, scramble="xor", arithmetic=arithmetic, icdf=icdf,
+                     output="moments").to_numpy()
+    assert np.allclose(mom[:, 1], got[:, -1, :].mean(axis=0), rtol=1e-13)
+
+
+def test_c5_terminal_moments_pseudo_match_oracle(oracle):
+    # C5 shape: GBM, 365 steps, pseudo-random, terminal moments only (reduced N for the CPU oracle)
+    times, N = grid(365), 1 << 13
+    ref = oracle.simulate(oracle.Universe(GBM_EQ, times), {"X1": 1.0}, N, "euler", "pseudo", seed=77)[:, -1, 0]
+    for icdf, arithmetic, tol in (("reference", "strict", 1e-12), ("fast", "fast", 1e-12)):
+        m = S.simulate(GBM_EQ, times, N, {"X1": 1.0}, "pseudo", "euler", seed=77, output="moments", icdf=icdf,
+                       arithmetic=arithmetic).to_numpy()[0]
+        assert m[0] == N
+        assert abs(m[1] / ref.mean() - 1) <= tol
+        assert abs(m[2] / ((ref - ref.mean()) ** 2).sum() - 1) <= 1e-9
+        term = S.simulate(GBM_EQ, times, N, {"X1": 1.0}, "pseudo", "euler", seed=77, output="terminal", icdf=icdf,
+                          arithmetic=arithmetic).to_numpy()[:, 0]
+        assert rel_err(term, ref) <= tol
+
+
+def test_full_size_c2_properties():
+    # C2 at BASELINE size (2^24 paths x 252 steps, 34 GB): size-independent properties instead of an oracle run
+    N, D = 1 << 24, 252
+    plan = S.Plan(S.Universe(GBM_EQ, grid(D)), "euler", "sobol", scramble="xor", icdf="fast", arithmetic="fast")
+    out = plan.run({"X1": 1.0}, N, seed=42)
+    assert bool((out[:, 0, 0] == 1.0).all())                                 # t0 row = initial value for every path
+    assert bool(torch.isfinite(out).all()) and bool((out > 0).all())
+    term = out[:, -1, 0]
+    mean = (1 + 0.05 / D) ** D
+    # a 2^24-point scrambled net integrates E[X_T] far below the MC standard error 0.1/sqrt(N) = 2.4e-5
+    assert abs(float(term.mean()) - mean) < 3e-6
+    # shard check at full size: paths [2^23, 2^23 + 4096) recomputed with an offset are bit-identical
+    lo = 1 << 23
+    part = plan.run({"X1": 1.0}, 4096, seed=42, scenario_offset=lo)
+    assert torch.equal(part, out[lo:lo + 4096])
+    # dimension-wise net property: in every time step the 2^24 uniforms hit each of 2^12 equal cells 2^12 times,
+    # hence each step's log-increment sample mean is tiny
+    inc = torch.log(out[:, 1:9, 0] / out[:, 0:8, 0]).mean(dim=0)
+    assert bool((inc.abs() < 2e-4).all())
+    del out
+    torch.cuda.empty_cache()

@@ -106,6 +106,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_leg(sample_paths: int, repeats: int = 1):
     """The reference's CPU algorithm (oracle port, OpenMP over scenarios like rayon in src/sim/mod.rs:41-43)
     on a bounded sample of the C2 workload.  Returns (path_steps_per_s, cores, seconds_per_pass)."""
@@ -116,31 +124,31 @@ def cpu_reference_leg(sample_paths: int, repeats: int = 1):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.simulate(U, INIT, sample_paths, "euler", "sobol", seed=SEED, scramble="xor")
+        orc.simulate(U, INIT, sample_paths, "euler", "sobol", seed=SEED, scramble="xor", nthreads=_host_threads())
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return sample_paths * D / best, orc.num_threads(), best
+    return sample_paths * D / best, _host_threads(), best
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 1 << 17
+    sample = 1 << 20                                     # ~1 s of CPU work per step on 16 cores
     W, K = max(args.warmup, 0), max(args.steps, 1)
     from oracle import oracle as orc
 
     orc.build()
     U = orc.Universe(GBM_EQ, TIMES)
+    cores = _host_threads()
     for _ in range(min(W, 1)):
-        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor")
+        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor", nthreads=cores)
     K = min(K, 5)
     t0 = time.perf_counter()
     for _ in range(K):
-        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor")
+        orc.simulate(U, INIT, sample, "euler", "sobol", seed=SEED, scramble="xor", nthreads=cores)
     dt = (time.perf_counter() - t0) / K
     value = sample * D / dt
-    cores = orc.num_threads()
     desc = f"{sample} paths x {D} steps of C2 per step (oracle C++ port of the reference algorithm, OpenMP, {cores} threads)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
@@ -277,7 +285,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 17)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 21)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -130,13 +130,10 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
 // 1 - p = (2 ~k + 1) * 2^-33, so min(p, 1-p) is a conditional bit flip of k.
 __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const double* s_table, int lane) {
     const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
-    const sde_u32 kw = k ^ (sde_u32)sgn;                     // top bit now clear; w = (2 kw + 1) * 2^-33
-    const int pos = 31 - __clz((int)kw);                     // leading one of kw (-1 when kw == 0: w = 2^-33 exactly)
-    // mantissa below the leading one of (kw:1), left aligned in 32 bits: (kw : 0x80000000) >> pos, low word
-    sde_u32 mh = __funnelshift_r(0x80000000u, kw, pos);
-    mh = (kw == 0u) ? 0u : mh;
-    // w = 1.m * 2^(pos - 32): exponent term eln2[h], h - 53 = pos - 32
-    double x = sde_icdf_as_core(mh >> 12, mh << 20, s_table + SDE_ICDF_LOG_DOUBLES + 21 + pos,
+    const sde_u32 j = ((k ^ (sde_u32)sgn) << 1) | 1u;        // w = min(p, 1-p) = j * 2^-33, j odd, 1 <= j < 2^32
+    const int pos = 31 - __clz((int)j);                      // leading one of j: w = 1.m * 2^(pos - 33)
+    const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned (pos = 0 -> 0)
+    double x = sde_icdf_as_core(mh >> 12, mh << 20, s_table + SDE_ICDF_LOG_DOUBLES + 20 + pos,     // h - 53 = pos - 33
                                 s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
     return __hiloint2double(xhi, __double2loint(x));

@@ -391,16 +391,20 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
             }
-            if (valid) {
+            {
+                // predicated (not branched) stores: dead lanes only exist in the first and last CTA
                 double* dst = my_row + (size_t)(tc + 1) * SDE_P;      // 32-byte aligned by the choice of gamma
+                const int live = valid ? 1 : 0;
 #pragma unroll
                 for (int q = 0; q < SDE_P; ++q) {
 #if SDE_ST256
-                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]),
-                                 "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+                    asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
+                                 ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
 #else
-                    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]) : "memory");
-                    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(dst + 4 * q + 2), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+                    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p st.global.v2.f64 [%0], {%1, %2}; }"
+                                 ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "r"(live) : "memory");
+                    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p st.global.v2.f64 [%0], {%1, %2}; }"
+                                 ::"l"(dst + 4 * q + 2), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
 #endif
                 }
             }

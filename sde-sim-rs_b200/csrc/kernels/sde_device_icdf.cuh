@@ -131,7 +131,8 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
 __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const double* s_table, int lane) {
     const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
     const sde_u32 j = ((k ^ (sde_u32)sgn) << 1) | 1u;        // w = min(p, 1-p) = j * 2^-33, j odd, 1 <= j < 2^32
-    const int pos = 31 - __clz((int)j);                      // leading one of j: w = 1.m * 2^(pos - 33)
+    int pos;                                                  // leading one of j (FLO): w = 1.m * 2^(pos - 33)
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(j));
     const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned (pos = 0 -> 0)
     double x = sde_icdf_as_core(mh >> 12, mh << 20, s_table + SDE_ICDF_LOG_DOUBLES + 20 + pos,     // h - 53 = pos - 33
                                 s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));

@@ -379,6 +379,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #endif
         };
+#if SDE_DIRECT
+        double* group_dst = my_row;                           // running store pointer of the step groups
+#endif
         auto group = [&](const int tc) __attribute__((always_inline)) {
             double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
 #pragma unroll
@@ -393,7 +396,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
             {
                 // predicated (not branched) stores: dead lanes only exist in the first and last CTA
-                double* dst = my_row + (size_t)(tc + 1) * SDE_P;      // 32-byte aligned by the choice of gamma
+                double* dst = group_dst;                      // = my_row + (tc + 1) P: 32-byte aligned by the choice of gamma
+                group_dst += 4 * SDE_P;
                 const int live = valid ? 1 : 0;
 #pragma unroll
                 for (int q = 0; q < SDE_P; ++q) {
@@ -439,6 +443,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 for (int j = 0; j < 3; ++j) if (j < g_eff) single(j, j);
             }
             int tc = t0 + g_eff;
+            group_dst = my_row + (size_t)(tc + 1) * SDE_P;
             const int t_hi = min(t0 + SDE_TT + g_eff, s_full);
             const int n_groups = t_hi > tc ? (t_hi - tc) >> 2 : 0;
 #pragma unroll 1

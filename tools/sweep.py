@@ -20,8 +20,7 @@ modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="refe
 which = sys.argv[1:] or ["fast"]
 out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
-grid = [("NTP", 2, tt, b, mb) for (tt, b, mb) in ((0, 256, 4), (84, 256, 4), (0, 128, 8), (64, 128, 8), (0, 128, 6), (0, 512, 2),
-                                                  (0, 256, 5), (28, 256, 4), (0, 256, 3))]
+grid = [("NTP", 2, tt, b, mb) for (tt, b, mb) in ((0, 256, 4), (0, 256, 3), (0, 128, 8), (64, 256, 4))]
 grid += [("NTP", 1, 0, 256, 2), ("TPN", 0, 0, 256, 4)]
 for mode in which:
     for layout, direct, tt, block, mb in grid:

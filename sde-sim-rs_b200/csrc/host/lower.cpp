@@ -288,9 +288,11 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
         size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
-        size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
+        auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        size_t stage = a16((size_t)ts * (4 + nslot) * 8) + (sobol ? a16((size_t)ts * KK * nw * 4) + (size_t)ts * KK * 32 * 4 : 0);
+        size_t scratch = (size_t)ts * 32 + (sobol ? (size_t)ts * KK * nw * 9 * 4 : 0);   // cp.async landing zone
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
-        return icdf + tile + 2 * stage + mom;
+        return icdf + tile + 2 * stage + scratch + mom;
     };
     if (opt.block <= 0 && !L.direct) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
     L.smem_bytes = smem_for(L.block);

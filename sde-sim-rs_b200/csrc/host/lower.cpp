@@ -288,18 +288,18 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
         size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
-        auto a16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-        size_t stage = a16((size_t)ts * (4 + nslot) * 8) + (sobol ? a16((size_t)ts * KK * nw * 4) + (size_t)ts * KK * 32 * 4 : 0);
-        size_t scratch = (size_t)ts * 32 + (sobol ? (size_t)ts * KK * nw * 9 * 4 : 0);   // cp.async landing zone
+        size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
-        return icdf + tile + 2 * stage + scratch + mom;
+        return icdf + tile + 2 * stage + mom;
     };
     if (opt.block <= 0 && !L.direct) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
     L.smem_bytes = smem_for(L.block);
     if (L.smem_bytes > 227 * 1024) throw ExprError{"model too large for the shared-memory staging tile (P = " + std::to_string(P) + ")"};
     {
-        // measured on B200 (tools/sweep.py): 4 CTAs x 256 threads at a 64-register cap beat 2-3 CTAs with more registers
-        const int regs_est = std::min(255, 52 + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
+        // measured on B200 (tools/sweep.py, profiles/r1_sweep_c2.json): with 4-step groups the kernel wants ~100 registers
+        // (the next tile's prefetched words stay in registers behind the last group); 2 CTAs x 256 threads at a
+        // 128-register cap beat 3-4 CTAs at 85 / 64 registers (409 vs 403 / 376 G path-steps/s on C2)
+        const int regs_est = std::min(255, (L.unr >= 4 ? 96 : 52) + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
         int by_regs = std::max(1, 65536 / (L.block * regs_est));
         int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / std::max<size_t>(L.smem_bytes, 1024));
         int by_threads = std::max(1, 2048 / L.block);

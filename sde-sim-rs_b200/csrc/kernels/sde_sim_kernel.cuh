@@ -90,21 +90,20 @@ struct SdeParams {
 #define SDE_STEP_LD (4 + SDE_NSLOT)
 
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
-//   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | cp.async landing zone | moment scratch
+//   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | moment scratch
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
 #define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0 && !SDE_DIRECT) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
-#define SDE_ALIGN16(x) (((x) + 15) & ~15)
-#define SDE_SMEM_STEP_BYTES SDE_ALIGN16(SDE_TS * SDE_STEP_LD * 8)
-#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? SDE_ALIGN16(SDE_TS * SDE_KK * SDE_NW * 4) : 0)
+#define SDE_SMEM_STEP_BYTES (SDE_TS * SDE_STEP_LD * 8)
+#define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * SDE_NW * 4) : 0)
 #define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * 32 * 4) : 0)
 #define SDE_SMEM_STAGE_BYTES (SDE_SMEM_STEP_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES)
-// landing zone of the asynchronous (cp.async) prefetch: raw {t, t+dt, dt, sqrt dt} per step and the 9 raw words
-// (8 nibble-table entries + digital-shift mask) of every Sobol CTA/warp-part entry; reduced into the stage buffer at commit
-#define SDE_SMEM_RAWSTEP_BYTES (SDE_TS * 32)
-#define SDE_SMEM_RAWBW_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * SDE_NW * 9 * 4) : 0)
-#define SDE_SMEM_SCRATCH_BYTES (SDE_SMEM_RAWSTEP_BYTES + SDE_SMEM_RAWBW_BYTES)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + 2 * SDE_SMEM_STAGE_BYTES + SDE_SMEM_SCRATCH_BYTES + SDE_SMEM_MOM_BYTES)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + 2 * SDE_SMEM_STAGE_BYTES + SDE_SMEM_MOM_BYTES)
+
+// prefetch register counts (compile-time): entries of each staged table owned by one thread
+#define SDE_PF_BW ((SDE_TS * SDE_KK * SDE_NW + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_LANE ((SDE_TS * SDE_KK * 32 + SDE_BLOCK - 1) / SDE_BLOCK)
+#define SDE_PF_STEP ((SDE_TS + SDE_BLOCK - 1) / SDE_BLOCK)
 
 struct SdeMoments { double n, mean, m2; };
 
@@ -129,18 +128,16 @@ __device__ __forceinline__ double sde_uniform_to_draw(double u, bool wiener, con
 #endif
 }
 
-// Asynchronous global -> shared copies (LDGSTS): the next tile's tables travel without occupying registers or
-// stalling the issuing warp; they are waited for only after the last step group of the current tile.
-__device__ __forceinline__ void sde_cp_async_4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void sde_cp_async_8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void sde_cp_async_16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void sde_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Registers that carry the next tile's staged data from the moment its loads are issued to the moment
+// they are written to shared memory (static indexing only).
+struct SdeTilePrefetch {
+    double st[SDE_PF_STEP][4];
+#if SDE_USES_SOBOL
+    sde_u32 bw[SDE_PF_BW][9];   // the 8 nibble-table words (+ digital-shift mask) of each entry; XORed at commit time so
+                                // that nothing waits on these loads while the last step group of the tile runs
+    sde_u32 ln[SDE_PF_LANE];
+#endif
+};
 
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
     extern __shared__ double4 sde_smem_raw[];
@@ -175,73 +172,82 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     sde_icdf_table_load(s_icdf, tid, SDE_BLOCK);
 #endif
 
-    // ---- staging of one tile's read-only data (see header).  issue(): asynchronous copies global -> shared
-    //      (lane-table slice straight into stage buffer `buf`, raw step data and raw Sobol words into the landing
-    //      zone); commit(): wait for this thread's copies, reduce them into stage buffer `buf`.
-    unsigned char* s_scratch = s_stage + 2 * SDE_SMEM_STAGE_BYTES;
-    double* s_rawstep = reinterpret_cast<double*>(s_scratch);
-    sde_u32* s_rawbw = reinterpret_cast<sde_u32*>(s_scratch + SDE_SMEM_RAWSTEP_BYTES);
-    (void)s_rawbw;
-    auto issue = [&](const int t0, const int buf) __attribute__((always_inline)) {
+    // ---- staging of one tile's read-only data (see header).  issue(): global loads into registers;
+    //      commit(): registers -> shared memory buffer `buf`.
+    auto issue = [&](const int t0, SdeTilePrefetch& pf) __attribute__((always_inline)) {
         const int nt = min(SDE_TS, S - t0);
-        for (int e = tid; e < nt; e += SDE_BLOCK) {
-            sde_cp_async_8(s_rawstep + 4 * e + 0, prm.times + t0 + e);
-            sde_cp_async_8(s_rawstep + 4 * e + 1, prm.times + t0 + e + 1);
-            sde_cp_async_8(s_rawstep + 4 * e + 2, prm.dts + t0 + e);
-            sde_cp_async_8(s_rawstep + 4 * e + 3, prm.sqrt_dts + t0 + e);
+#pragma unroll
+        for (int i = 0; i < SDE_PF_STEP; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < nt) {
+                pf.st[i][0] = __ldg(prm.times + t0 + e);
+                pf.st[i][1] = __ldg(prm.times + t0 + e + 1);
+                pf.st[i][2] = __ldg(prm.dts + t0 + e);
+                pf.st[i][3] = __ldg(prm.sqrt_dts + t0 + e);
+            }
         }
 #if SDE_USES_SOBOL
         const int nd = nt * SDE_K;
         const size_t d0 = (size_t)t0 * SDE_K;
-        for (int e = tid; e < nd * SDE_NW; e += SDE_BLOCK) {
-            // x_d(n_cta + warp part) = XOR over the nibbles of gray(n) of a 16-entry table: independent words
-            const int dl = e / SDE_NW, w = e - dl * SDE_NW;
-#if SDE_DIRECT
-            const sde_u32 nw = (sde_u32)n_cta + 128u * (sde_u32)(w >> 2) + (sde_u32)(w & 3);
-#else
-            const sde_u32 nw = (sde_u32)n_cta + 32u * (sde_u32)w;
-#endif
-            const sde_u32 g = nw ^ (nw >> 1);
-            const sde_u32* tab = prm.sobol_nib + (d0 + dl) * 128;
 #pragma unroll
-            for (int q = (SDE_DIRECT ? 0 : 1); q < 8; ++q) sde_cp_async_4(s_rawbw + e * 9 + q, tab + q * 16 + ((g >> (4 * q)) & 15u));
-#if SDE_RNG == 2
-            sde_cp_async_4(s_rawbw + e * 9 + 8, prm.xor_masks + d0 + dl);    // the digital shift of this dimension, folded in
+        for (int i = 0; i < SDE_PF_BW; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) pf.bw[i][q] = 0u;
+            if (e < nd * SDE_NW) {
+                // x_d(n_cta + warp part) = XOR over the nibbles of gray(n) of a 16-entry table: independent loads
+                const int dl = e / SDE_NW, w = e - dl * SDE_NW;
+#if SDE_DIRECT
+                const sde_u32 nw = (sde_u32)n_cta + 128u * (sde_u32)(w >> 2) + (sde_u32)(w & 3);
+#else
+                const sde_u32 nw = (sde_u32)n_cta + 32u * (sde_u32)w;
 #endif
+                const sde_u32 g = nw ^ (nw >> 1);
+                const sde_u32* tab = prm.sobol_nib + (d0 + dl) * 128;
+#pragma unroll
+                for (int q = (SDE_DIRECT ? 0 : 1); q < 8; ++q) pf.bw[i][q] = __ldg(tab + q * 16 + ((g >> (4 * q)) & 15u));
+#if SDE_RNG == 2
+                pf.bw[i][8] = __ldg(prm.xor_masks + d0 + dl);      // the digital shift of this dimension, folded in
+#endif
+            }
         }
-        {   // x_d(lane): contiguous slice of the global lane table, 16 bytes per copy
-            sde_u32* ln = reinterpret_cast<sde_u32*>(s_stage + buf * SDE_SMEM_STAGE_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_BW_BYTES);
-            const sde_u32* src = prm.sobol_lane + d0 * 32;
-            for (int e = tid; e < nd * 8; e += SDE_BLOCK) sde_cp_async_16(ln + 4 * e, src + 4 * e);
+#pragma unroll
+        for (int i = 0; i < SDE_PF_LANE; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            pf.ln[i] = (e < nd * 32) ? __ldg(prm.sobol_lane + d0 * 32 + e) : 0u;
         }
 #endif
     };
-    auto commit = [&](const int t0, const int buf) __attribute__((always_inline)) {
-        sde_cp_async_wait_all();                              // this thread's copies have landed (it only reads its own)
+    auto commit = [&](const int t0, const SdeTilePrefetch& pf, const int buf) __attribute__((always_inline)) {
         const int nt = min(SDE_TS, S - t0);
         double* st = reinterpret_cast<double*>(s_stage + buf * SDE_SMEM_STAGE_BYTES);
-        for (int e = tid; e < nt; e += SDE_BLOCK) {
-            double* rec = st + e * SDE_STEP_LD;
-            const double a = s_rawstep[4 * e], b = s_rawstep[4 * e + 1], c = s_rawstep[4 * e + 2], d = s_rawstep[4 * e + 3];
-            rec[0] = a; rec[1] = b; rec[2] = c; rec[3] = d;
-#if SDE_NSLOT > 0
-            double slots[SDE_NSLOT];
-            sde_model_step_consts(a, b, c, d, slots);
 #pragma unroll
-            for (int q = 0; q < SDE_NSLOT; ++q) rec[4 + q] = slots[q];
+        for (int i = 0; i < SDE_PF_STEP; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < nt) {
+                double* rec = st + e * SDE_STEP_LD;
+                rec[0] = pf.st[i][0]; rec[1] = pf.st[i][1]; rec[2] = pf.st[i][2]; rec[3] = pf.st[i][3];
+#if SDE_NSLOT > 0
+                double slots[SDE_NSLOT];
+                sde_model_step_consts(pf.st[i][0], pf.st[i][1], pf.st[i][2], pf.st[i][3], slots);
+#pragma unroll
+                for (int q = 0; q < SDE_NSLOT; ++q) rec[4 + q] = slots[q];
 #endif
+            }
         }
 #if SDE_USES_SOBOL
         sde_u32* bw = reinterpret_cast<sde_u32*>(s_stage + buf * SDE_SMEM_STAGE_BYTES + SDE_SMEM_STEP_BYTES);
-        const int nd = nt * SDE_K;
-        for (int e = tid; e < nd * SDE_NW; e += SDE_BLOCK) {
-            sde_u32 x = 0;
+        sde_u32* ln = bw + SDE_SMEM_BW_BYTES / 4;
 #pragma unroll
-            for (int q = (SDE_DIRECT ? 0 : 1); q < 8; ++q) x ^= s_rawbw[e * 9 + q];
-#if SDE_RNG == 2
-            x ^= s_rawbw[e * 9 + 8];
-#endif
-            bw[e] = x;
+        for (int i = 0; i < SDE_PF_BW; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < SDE_TS * SDE_KK * SDE_NW)
+                bw[e] = ((pf.bw[i][0] ^ pf.bw[i][1]) ^ (pf.bw[i][2] ^ pf.bw[i][3])) ^ ((pf.bw[i][4] ^ pf.bw[i][5]) ^ (pf.bw[i][6] ^ pf.bw[i][7])) ^ pf.bw[i][8];
+        }
+#pragma unroll
+        for (int i = 0; i < SDE_PF_LANE; ++i) {
+            const int e = tid + i * SDE_BLOCK;
+            if (e < SDE_TS * SDE_KK * 32) ln[e] = pf.ln[i];
         }
 #endif
     };
@@ -279,9 +285,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     }
 #endif
 
-    // tile 0 is staged synchronously
-    issue(0, 0);
-    commit(0, 0);
+    {   // tile 0 is staged synchronously
+        SdeTilePrefetch pf;
+        issue(0, pf);
+        commit(0, pf, 0);
+    }
     __syncthreads();
 
     int buf = 0;
@@ -425,6 +433,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
 
         const bool more = t0 + SDE_TT < S;                    // another tile follows: prefetch it behind the last group
+        SdeTilePrefetch pf;
 #if SDE_DIRECT
         {
             // this warp's steps in tile k: [t0 + gamma, t0 + TT + gamma), clipped to the last full group; the first
@@ -441,7 +450,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             const int n_groups = t_hi > tc ? (t_hi - tc) >> 2 : 0;
 #pragma unroll 1
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += 4) group(tc);
-            if (more) issue(t0 + SDE_TT, buf ^ 1);
+            if (more) issue(t0 + SDE_TT, pf);
             if (n_groups > 0) { group(tc); tc += 4; }
             if (!more) {
 #pragma unroll
@@ -455,14 +464,14 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             int tc = t0;
 #pragma unroll 1
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += SDE_UNR) group(tc);
-            if (more) issue(t0 + SDE_TT, buf ^ 1);
+            if (more) issue(t0 + SDE_TT, pf);
             if (n_groups > 0) { group(tc); tc += SDE_UNR; }
 #pragma unroll
             for (int j = 0; j < SDE_UNR - 1; ++j)
                 if (tc + j < t_end) single(tc + j, j);
         }
 #endif
-        if (more) commit(t0 + SDE_TT, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
+        if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
 
 #if SDE_OUT == 0 && !SDE_DIRECT
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM

@@ -20,8 +20,7 @@ modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="refe
 which = sys.argv[1:] or ["fast"]
 out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
-grid = [("NTP", 2, tt, b, mb) for (tt, b, mb) in ((0, 256, 4), (0, 256, 3), (0, 128, 8), (64, 256, 4))]
-grid += [("NTP", 1, 0, 256, 2), ("TPN", 0, 0, 256, 4)]
+grid = [("NTP", 2, tt, b, mb) for (tt, b, mb) in ((0, 256, 4), (0, 256, 3), (0, 256, 2), (64, 256, 3), (28, 256, 3))]
 for mode in which:
     for layout, direct, tt, block, mb in grid:
         try:

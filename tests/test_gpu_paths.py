@@ -265,3 +265,53 @@ def test_full_size_c2_properties():
     assert bool((inc.abs() < 2e-4).all())
     del out
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------- ragged shapes (tile / group / sector edges)
+THREE_EQ = ["dA = ( 0.3 * (1.0 - A) ) * dt + ( 0.2 ) * dW1",
+            "dB = ( 0.1 * B ) * dt + ( 0.3 * B ) * dW2",
+            "dC = ( A - C ) * dt + ( 0.1 * B ) * dW1"]
+THREE_INIT = {"A": 0.5, "B": 2.0, "C": -1.0}
+
+
+@pytest.mark.parametrize("steps", [1, 2, 3, 4, 5, 7, 8, 35, 36, 37, 40, 73, 145])
+def test_ragged_step_counts_all_store_paths(oracle, steps):
+    # the direct sector-store path shifts every warp's step groups by gamma in 0..3 and handles the first gamma and
+    # the last <= 3 steps on their own; tiles are 32-36 steps: cover every residue, both store paths, odd offsets
+    for eqs, init, D in ((GBM_EQ, {"X1": 1.0}, 252), (HESTON_EQ, {"S": 100.0, "v": 0.04}, 1000), (THREE_EQ, THREE_INIT, 50)):
+        times, N, off = grid(D, steps), 777, 1021
+        ref = oracle.simulate(oracle.Universe(eqs, times), init, N, "euler", "sobol", seed=21, scramble="xor", scenario_offset=off)
+        for direct in (1, 2):
+            plan = S.Plan(S.Universe(eqs, times), "euler", "sobol", scramble="xor", ntp_direct=direct)
+            got = plan.run(init, N, seed=21, scenario_offset=off).cpu().numpy()
+            assert rel_err(got, ref) <= 1e-12, (steps, direct, len(eqs), rel_err(got, ref))
+
+
+@pytest.mark.parametrize("N,off", [(1, 0), (2, 3), (5, 250), (251, 5), (256, 251), (257, 0), (1000, 4091)])
+def test_ragged_scenario_counts_and_offsets(oracle, N, off):
+    times = grid(252, 41)
+    for rng_method, scramble in (("sobol", "xor"), ("pseudo", "none")):
+        ref = oracle.simulate(oracle.Universe(GBM_EQ, times), {"X1": 1.0}, N, "runge-kutta", rng_method, seed=8,
+                              scramble=scramble if rng_method == "sobol" else "cp_shift_per_path", scenario_offset=off)
+        got = S.simulate(GBM_EQ, times, N, {"X1": 1.0}, rng_method, "runge-kutta", seed=8,
+                         scramble=scramble if rng_method == "sobol" else "cp_shift_per_path", scenario_offset=off).to_numpy()
+        assert rel_err(got, ref) <= 1e-12
+
+
+def test_pure_drift_and_zero_term_processes(oracle):
+    # K = 0 (no stochastic factor), a zero-term SDE (`delta = ...` quirk, util.rs:80-82) and an algebraic process
+    eqs = ["dX = ( 0.5 * X ) * dt", "delta = 1.0", "Y = X * 2.0 + t"]
+    times, init = grid(10, 12), {"X": 1.0, "elta": 3.0, "Y": 7.0}
+    ref = oracle.simulate(oracle.Universe(eqs, times), init, 9, "euler", "pseudo", seed=1)
+    got = S.simulate(eqs, times, 9, init, "pseudo", "euler", seed=1).to_numpy()
+    assert rel_err(got[:, :, [0, 2]], ref[:, :, [0, 2]]) <= 1e-12 and np.array_equal(got[:, :, 1], ref[:, :, 1])
+    with pytest.raises(ValueError, match="runge-kutta needs"):
+        S.simulate(eqs, times, 9, init, "pseudo", "runge-kutta", seed=1)
+
+
+def test_nonuniform_time_grid(oracle):
+    times = [0.0, 0.01, 0.015, 0.1, 0.1000001, 0.5, 2.0, 2.5]
+    for scheme in ("euler", "runge-kutta"):
+        ref = oracle.simulate(oracle.Universe(HESTON_EQ, times), {"S": 100.0, "v": 0.04}, 300, scheme, "sobol", seed=2, scramble="xor")
+        got = S.simulate(HESTON_EQ, times, 300, {"S": 100.0, "v": 0.04}, "sobol", scheme, seed=2, scramble="xor").to_numpy()
+        assert rel_err(got, ref) <= 1e-12

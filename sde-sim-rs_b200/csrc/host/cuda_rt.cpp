@@ -3,9 +3,14 @@
 
 #include <dlfcn.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #define SDE_STR2(x) #x
 #define SDE_STR(x) SDE_STR2(x)
@@ -160,6 +165,45 @@ int sm_count(int device) {
     return n;
 }
 
+namespace {
+// ---- compiled-kernel cache: the same model lowered with the same options compiles once per process and,
+//      when $SDE_B200_CACHE names a directory, once per machine (cubins keyed by source + headers + NVRTC version).
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+std::mutex g_cache_mu;
+std::unordered_map<uint64_t, std::vector<char>> g_cubin_cache;
+
+std::string cache_dir() {
+    // opt-in: only when the caller names a directory (the Python package points it inside its own build/ tree)
+    if (std::getenv("SDE_B200_NO_DISK_CACHE")) return "";
+    const char* d = std::getenv("SDE_B200_CACHE");
+    return d ? d : "";
+}
+bool read_file(const std::string& path, std::vector<char>* out) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    bool ok = n > 0;
+    if (ok) { out->resize((size_t)n); ok = std::fread(out->data(), 1, (size_t)n, f) == (size_t)n; }
+    std::fclose(f);
+    return ok;
+}
+void write_file_atomic(const std::string& dir, const std::string& path, const std::vector<char>& data) {
+    ::mkdir(dir.c_str(), 0755);                              // best effort; parents are expected to exist
+    std::string tmp = path + ".tmp." + std::to_string((long)::getpid());
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    bool ok = std::fwrite(data.data(), 1, data.size(), f) == data.size();
+    std::fclose(f);
+    if (ok) std::rename(tmp.c_str(), path.c_str()); else std::remove(tmp.c_str());
+}
+}  // namespace
+
 std::vector<char> nvrtc_compile(const std::string& source, const std::string& name, std::string* log) {
     const NvrtcApi& n = nvrtc();
     struct H { const char* name; const char* b; const char* e; };
@@ -170,6 +214,33 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
         {"sde_icdf_tables.cuh", sde_blob_icdf_tables_cuh_begin, sde_blob_icdf_tables_cuh_end},
         {"sde_expr_helpers.cuh", sde_blob_expr_helpers_cuh_begin, sde_blob_expr_helpers_cuh_end},
     };
+    NvrtcState& nst = nvrtc_state();
+    // st.global.v4.f64 (256-bit) needs the CUDA 12.9 ptxas; older NVRTC falls back to two 128-bit stores
+    const bool st256 = nst.major > 12 || (nst.major == 12 && nst.minor >= 9);
+
+    uint64_t key = fnv1a(source.data(), source.size());
+    for (const H& h : hs) key = fnv1a(h.b, (size_t)(h.e - h.b), key);
+    const int ver[3] = {nst.major, nst.minor, st256 ? 1 : 0};
+    key = fnv1a(ver, sizeof ver, key);
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_cubin_cache.find(key);
+        if (it != g_cubin_cache.end()) { if (log) *log = "(cached in memory)"; return it->second; }
+    }
+    const std::string dir = cache_dir();
+    char hex[32];
+    std::snprintf(hex, sizeof hex, "%016llx", (unsigned long long)key);
+    const std::string path = dir.empty() ? "" : dir + "/" + hex + ".cubin";
+    if (!path.empty()) {
+        std::vector<char> cached;
+        if (read_file(path, &cached) && cached.size() > 64 && std::memcmp(cached.data(), "\x7f" "ELF", 4) == 0) {
+            std::lock_guard<std::mutex> lock(g_cache_mu);
+            g_cubin_cache[key] = cached;
+            if (log) *log = "(cached on disk: " + path + ")";
+            return cached;
+        }
+    }
+
     std::vector<std::string> bodies;
     std::vector<const char*> names, ptrs;
     for (const H& h : hs) bodies.emplace_back(h.b, h.e);
@@ -177,9 +248,6 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
     nvrtcProgram prog;
     nvrtcResult r = n.nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), (int)names.size(), ptrs.data(), names.data());
     if (r != NVRTC_SUCCESS) throw CudaError{std::string("nvrtcCreateProgram: ") + n.nvrtcGetErrorString(r)};
-    // st.global.v4.f64 (256-bit) needs the CUDA 12.9 ptxas; older NVRTC falls back to two 128-bit stores
-    NvrtcState& nst = nvrtc_state();
-    const bool st256 = nst.major > 12 || (nst.major == 12 && nst.minor >= 9);
     const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", st256 ? "-DSDE_ST256=1" : "-DSDE_ST256=0"};
     r = n.nvrtcCompileProgram(prog, 4, opts);
     size_t ls = 0;
@@ -197,6 +265,11 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
     n.nvrtcGetCUBIN(prog, cubin.data());
     n.nvrtcDestroyProgram(&prog);
     if (cs == 0) throw CudaError{"NVRTC produced an empty cubin"};
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        g_cubin_cache[key] = cubin;
+    }
+    if (!path.empty()) write_file_atomic(dir, path, cubin);
     return cubin;
 }
 

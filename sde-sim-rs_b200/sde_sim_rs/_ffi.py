@@ -90,6 +90,14 @@ SIGNATURES = {
 
 _lib = None
 
+# compiled-kernel cache of the library (cubins keyed by generated source + kernel headers + NVRTC version):
+# kept inside the package's own build/ tree unless the caller chose a place
+_CACHE_DIR = os.environ.setdefault("SDE_B200_CACHE", os.path.join(os.path.dirname(_HERE), "build", "jit_cache"))
+try:
+    os.makedirs(_CACHE_DIR, exist_ok=True)
+except OSError:
+    pass
+
 
 def lib():
     """Load libsde_b200.so (fails loudly when the native library has not been built)."""

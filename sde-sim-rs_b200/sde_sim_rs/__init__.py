@@ -253,6 +253,19 @@ class Filtration:
 
         return pd.DataFrame(self.columns())
 
+    def to_arrow(self):
+        """Arrow table with the reference's schema (scenario:int32, time:float64, process_name:string, value:float64);
+        the value column wraps the host copy of the dense buffer without another copy.  pyo3-polars hands the
+        reference's frame to Python as exactly these Arrow buffers (src/py_binding.rs:55)."""
+        import pyarrow as pa
+
+        c = self.columns()
+        names = pa.DictionaryArray.from_arrays(
+            pa.array(np.tile(np.arange(len(self.process_names), dtype=np.int32), c["value"].size // len(self.process_names))),
+            pa.array(self.process_names)).cast(pa.string())
+        return pa.table({"scenario": pa.array(c["scenario"], type=pa.int32()), "time": pa.array(c["time"]),
+                         "process_name": names, "value": pa.array(c["value"])})
+
     def to_polars(self):
         import polars as pl  # not in this image; present wherever the reference's callers run
 

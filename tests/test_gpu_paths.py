@@ -140,6 +140,9 @@ def test_long_format_columns_match_reference_layout():
     assert c["value"][:2].tolist() == [100.0, 0.04]
     df = f.to_pandas()
     assert list(df.columns) == ["scenario", "time", "process_name", "value"] and len(df) == N * 4 * 2
+    tb = f.to_arrow()
+    assert [str(t) for t in tb.schema.types] == ["int32", "double", "string", "double"] and tb.num_rows == N * 4 * 2
+    assert tb.column("process_name")[1].as_py() == "v" and tb.column("value")[0].as_py() == 100.0
 
 
 def test_pseudo_mc_statistics_match_closed_form():
@@ -315,3 +318,16 @@ def test_nonuniform_time_grid(oracle):
         ref = oracle.simulate(oracle.Universe(HESTON_EQ, times), {"S": 100.0, "v": 0.04}, 300, scheme, "sobol", seed=2, scramble="xor")
         got = S.simulate(HESTON_EQ, times, 300, {"S": 100.0, "v": 0.04}, "sobol", scheme, seed=2, scramble="xor").to_numpy()
         assert rel_err(got, ref) <= 1e-12
+
+
+def test_run_host_chunk_boundaries():
+    # sde_plan_run_host cuts the scenarios into ~512 MiB chunks (double-buffered D2H); chunk seams must not show
+    times, init = grid(252), {"X1": 1.0}
+    N = 600_011                                             # > 2 chunks of 265 216 paths for [N, 253, 1]
+    plan = S.Plan(S.Universe(GBM_EQ, times), "euler", "sobol", scramble="xor", icdf="fast", arithmetic="fast")
+    dev = plan.run(init, N, seed=4, scenario_offset=123)
+    host = torch.empty((N, 253, 1), dtype=torch.float64).pin_memory()
+    plan.run_host(init, N, seed=4, scenario_offset=123, out=host)
+    assert torch.equal(host, dev.cpu())
+    term_plan = S.Plan(S.Universe(GBM_EQ, times), "euler", "pseudo", output="terminal")
+    assert np.array_equal(term_plan.run_host(init, 70_001, seed=4), term_plan.run(init, 70_001, seed=4).cpu().numpy())

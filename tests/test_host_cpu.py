@@ -168,3 +168,20 @@ def test_moments_merge_matches_numpy():
     assert np.allclose(m[:, 1], flat.mean(axis=1), rtol=1e-14)
     assert np.allclose(m[:, 2], ((flat - flat.mean(axis=1, keepdims=True)) ** 2).sum(axis=1), rtol=1e-12)
     assert np.array_equal(S.merge_moments(np.concatenate([np.zeros((1, 2, 3)), shards])), m)   # empty shard is neutral
+
+
+def test_filtration_long_format_views_cpu():
+    # the reference's four columns (src/filtration.rs:108-113) rendered from a dense [N, T, P] buffer (CPU tensor here)
+    import torch
+
+    vals = torch.arange(2 * 3 * 2, dtype=torch.float64).reshape(2, 3, 2)
+    f = S.Filtration(vals, np.array([0.0, 0.5, 1.0]), ["S", "v"], output="paths", layout="NTP", scenario_offset=7)
+    c = f.columns()
+    assert c["scenario"].dtype == np.int32 and c["scenario"].tolist() == [7] * 6 + [8] * 6
+    assert c["time"].tolist() == [0.0, 0.0, 0.5, 0.5, 1.0, 1.0] * 2
+    assert c["process_name"].tolist() == ["S", "v"] * 6 and c["value"].tolist() == list(map(float, range(12)))
+    assert list(f.to_pandas().columns) == ["scenario", "time", "process_name", "value"]
+    tb = f.to_arrow()
+    assert [str(t) for t in tb.schema.types] == ["int32", "double", "string", "double"] and tb.num_rows == 12
+    tpn = S.Filtration(vals.permute(1, 2, 0).contiguous(), np.array([0.0, 0.5, 1.0]), ["S", "v"], output="paths", layout="TPN")
+    assert np.array_equal(tpn.columns()["value"], c["value"])

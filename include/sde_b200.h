@@ -97,7 +97,8 @@ typedef struct sde_options {
     int32_t tile_steps;       /* 0 = auto; time-tile length override (tuning)                       */
     int32_t block_threads;    /* 0 = auto                                                           */
     int32_t min_blocks;       /* 0 = auto; CTAs per SM promised to the compiler (tuning)            */
-    int32_t ntp_direct;       /* 0 = auto; 1 = force the shared-memory transpose for SDE_LAYOUT_NTP paths; 2 = force direct sector stores */
+    int32_t ntp_direct;       /* SDE_LAYOUT_NTP paths: 0 = auto; 1 = shared-memory transpose; 2 = direct sector stores from the
+                               * time-tiled kernel; 3 = persistent-warp kernel with resident tables (Sobol xor / none only)        */
 } sde_options;
 
 void sde_options_default(sde_options* o);

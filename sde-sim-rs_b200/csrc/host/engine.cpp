@@ -159,6 +159,14 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
     if (uses_sobol(opt_.lower.rng) && dims > 0) {
         std::vector<uint32_t> V, lane, nib;
         sobol_tables((uint32_t)dims, V, lane, &nib, low_.direct ? 4u : 1u);
+        if (low_.resident) {
+            // sde_sim_resident.cuh reads the nibble table dimension-fastest: [8][16][ld], ld = dims rounded up to 32
+            const size_t ld = (dims + 31) & ~(size_t)31;
+            std::vector<uint32_t> nt(128 * ld, 0u);
+            for (size_t dd = 0; dd < dims; ++dd)
+                for (size_t qv = 0; qv < 128; ++qv) nt[qv * ld + dd] = nib[dd * 128 + qv];
+            nib.swap(nt);
+        }
         d_nib_.upload(nib.data(), nib.size() * 4);
         d_lane_.upload(lane.data(), lane.size() * 4);
         if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 4);
@@ -245,8 +253,15 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
     prm.sobol_nib = d_nib_.ptr(); prm.sobol_lane = d_lane_.ptr(); prm.xor_masks = d_masks_.ptr();
     prm.inject = (CUdeviceptr)d_inject;
     prm.out = (CUdeviceptr)d_out;
-    const uint64_t grid = (first_n + n - prm.n_base + block - 1) / block;
-    if (grid == 0) return;
+    uint64_t grid = (first_n + n - prm.n_base + block - 1) / block;
+    if (low_.resident) {
+        // persistent warps: one work item = 32 paths (lane stride 4 inside a 128-path block), see sde_sim_resident.cuh
+        const uint64_t base128 = first_n & ~127ull;
+        const uint64_t items = 4 * ((first_n + n - base128 + 127) / 128);
+        const uint64_t warps = block / 32;
+        grid = std::min<uint64_t>((items + warps - 1) / warps, (uint64_t)sm_count(opt_.device) * (uint64_t)low_.min_blocks);
+    }
+    if (grid == 0 || n == 0) return;
     if (grid > 0x7fffffffull) throw ExprError{"too many scenarios for one launch"};
     if (opt_.lower.out == OUT_MOMENTS) {
         size_t need = (size_t)grid * u_.P() * 3 * 8;

@@ -2,6 +2,7 @@
 #include "lower.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <sstream>
 
@@ -264,7 +265,34 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
     // full paths in reference order: straight from registers as aligned 256-bit stores when a group is 4 steps
     // and no ChaCha block alignment ties groups to the time origin; otherwise through the shared-memory transpose
-    L.direct = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && (L.block % 128) == 0 && P <= 8 && opt.direct != 0;
+    const bool sector_stores_ok = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && P <= 8 && opt.direct != 0;
+    L.direct = sector_stores_ok && (L.block % 128) == 0;
+    // Sobol-driven full paths whose tables fit in shared memory for the whole time grid: persistent warps, no time tiles
+    {
+        const int S = u.T() - 1;
+        auto resident_smem = [&](int block, int nslot_) {     // mirrors the SDE_SMEM_* macros of sde_sim_resident.cuh
+            const size_t sk = (size_t)S * K;
+            size_t icdf = (opt.icdf == 1) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;
+            return icdf + (size_t)S * (4 + nslot_) * 8 + sk * 128 + (size_t)(block / 32) * ((sk + 3) & ~(size_t)3) * 4;
+        };
+        const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
+        if (eligible && opt.direct != 1) {
+            // 12 warps per SM (3 per scheduler) is the measured optimum on B200: the kernel is bound by FP64-pipe and
+            // issue contention, not latency; more resident warps only add load/store-pipe queueing
+            int block = opt.block > 0 ? opt.block : 384;
+            block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
+            while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
+            if (resident_smem(block, nslot) <= 200 * 1024) {
+                L.resident = true;
+                L.direct = true;
+                L.block = block;
+                L.smem_bytes = resident_smem(block, nslot);
+            }
+        }
+        if (opt.direct == 2 && !L.resident)
+            throw ExprError{"the persistent-warp kernel needs Sobol (xor / none) full-path NTP output, K <= 2 and (T-1)*K*128 B of shared memory"};
+    }
+    if (!L.resident) {
     int tt = opt.tile_steps;
     if (tt <= 0) {
         tt = 32;
@@ -307,6 +335,14 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         if (opt.min_blocks > 0) L.min_blocks = std::min(opt.min_blocks, std::min(by_smem, by_threads));
     }
 
+    } else {
+        const int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / (L.smem_bytes + 1024));
+        const int by_threads = std::max(1, 2048 / L.block);
+        const int by_regs = std::max(1, 65536 / (L.block * 64));   // the step loop wants 64 registers (no spills at 64)
+        L.min_blocks = std::max(1, std::min({by_smem, by_threads, by_regs}));
+        if (opt.min_blocks > 0) L.min_blocks = std::min(opt.min_blocks, std::min(by_smem, by_threads));
+        L.tt = u.T() - 1;
+    }
     // ---- translation unit
     std::ostringstream s;
     s << "// Generated by libsde_b200 (csrc/host/lower.cpp) — model lowered from equation strings.\n";
@@ -322,6 +358,16 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
+    if (L.resident) {
+        s << "#define SDE_S " << (u.T() - 1) << "\n";
+        if (std::getenv("SDE_B200_DEBUG_NOSTORE")) s << "#define SDE_DEBUG_NOSTORE 1\n";                                                  // profiling aid
+        if (const char* g = std::getenv("SDE_B200_RES_PIPE")) s << "#define SDE_RES_PIPE " << (std::atoi(g) ? 1 : 0) << "\n";          // tuning
+        // steps per unrolled group: 8 (two sector stores per lane) for one-factor one-process models, else 4
+        // (measured on B200, C2: 449 vs 440 G path-steps/s); SDE_B200_RES_GRP overrides for tuning
+        int grp = (K == 1 && P == 1 && u.T() - 1 >= 32) ? 8 : 4;
+        if (const char* g = std::getenv("SDE_B200_RES_GRP")) grp = std::atoi(g) == 8 ? 8 : 4;
+        s << "#define SDE_RES_GRP " << grp << "\n";
+    }
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
@@ -343,7 +389,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "    const double t_cur = ss[0], t_next = ss[1], dt = ss[2], sqrt_dt = ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
     s << gen.prelude() << body.str();
-    s << "}\n#include \"sde_sim_kernel.cuh\"\n";
+    s << "}\n#include \"" << (L.resident ? "sde_sim_resident.cuh" : "sde_sim_kernel.cuh") << "\"\n";
     L.source = s.str();
     return L;
 }

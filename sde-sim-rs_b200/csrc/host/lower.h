@@ -25,7 +25,8 @@ struct LowerOptions {
     int block = 0;           // 0 = auto
     int tile_steps = 0;      // 0 = auto
     int min_blocks = 0;      // 0 = auto: CTAs per SM promised to the compiler (__launch_bounds__)
-    int direct = -1;         // -1 = auto, 0/1 = force the shared-memory transpose / direct sector-store path for NTP paths
+    int direct = -1;         // NTP paths: -1 = auto, 0 = shared-memory transpose, 1 = direct sector stores (tiled kernel),
+                             // 2 = persistent-warp kernel with resident tables (sde_sim_resident.cuh)
 };
 
 struct Lowered {
@@ -37,6 +38,7 @@ struct Lowered {
     int unr = 1;             // steps unrolled per loop trip (multiple of ch)
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
     bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
+    bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory
     bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)
 };
 

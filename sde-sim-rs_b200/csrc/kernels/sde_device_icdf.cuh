@@ -59,11 +59,14 @@ __device__ __forceinline__ double sde_rcp_approx(double a) {
 #define SDE_ICDF_LOG_DOUBLES (128 * 2 * SDE_ICDF_TABLE_REPL)
 #define SDE_ICDF_TABLE_DOUBLES (SDE_ICDF_LOG_DOUBLES + 64)
 
-__device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, int nthreads) {
+// y_offset is added to every -2 ln c entry: SDE_ICDF_Y_OFFSET_K32 for kernels that form the exponent term
+// arithmetically (sde_icdf_normal_fast_k32s), 0 for the ones that read it from the eln2 table.
+#define SDE_ICDF_Y_OFFSET_K32 134.47055302862938   /* 194 ln 2 = 66 ln 2 (w = 1.m 2^(pos-33)) + 128 ln 2 (D = 32 + pos/2) */
+__device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, int nthreads, double y_offset = 0.0) {
     for (int i = tid; i < 128 * SDE_ICDF_TABLE_REPL; i += nthreads) {
         const int idx = i / SDE_ICDF_TABLE_REPL;
         s_table[2 * i] = sde_icdf_log_table[idx][0];
-        s_table[2 * i + 1] = sde_icdf_log_table[idx][1];
+        s_table[2 * i + 1] = sde_icdf_log_table[idx][1] + y_offset;
     }
     for (int h = tid; h < 64; h += nthreads) s_table[SDE_ICDF_LOG_DOUBLES + h] = (double)(h - 53) * -1.3862943611198906;
 }
@@ -75,7 +78,9 @@ __constant__ double sde_kc[12] = {
     -0x1.55560888fbbc1p-1,  // 1  a2  } a1 = 1, a0 = -2 exact  (max |err| 4.9e-14 absolute in -2 ln w)
     SDE_AS_C2, SDE_AS_C1, SDE_AS_C0,       // 2..4
     SDE_AS_D3, SDE_AS_D2, SDE_AS_D1,       // 5..7
-    1.5, 0.0, 0.0, 0.0};
+    0.375,                                 // 8   3/8 of the cubic square-root step
+    -2.772588722239781,                    // 9   -4 ln 2: exponent term of the arithmetic variant
+    0.0, 0.0};
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
@@ -85,30 +90,46 @@ __constant__ double sde_kc[12] = {
 //   sqrt      rsqrt.approx.f64 seed (it only sees the high word: rel ~2^-20) + one cubic step           5
 //   N/D       Horner with FMA (2 + 3), rcp.approx.f64 seed + one cubic step, t - q                      10
 // Stated tolerance of the whole map against the REFERENCE evaluation: |dz| <= 5e-13 absolute.
-__device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, const double* eterm, const double* s_table_lane) {
-    const double m = __hiloint2double((int)(mb_hi | 0x3ff00000u), (int)mb_lo);       // in [1, 2)
-    // s_table_lane = s_table + (lane & 7) * 2: the copy of the log table this lane's bank group owns
-    const double2 tc = *reinterpret_cast<const double2*>(s_table_lane + (mb_hi >> 13) * (2 * SDE_ICDF_TABLE_REPL));
+// The MUFU seeds only define the high word of their result; PTX zero-fills the low word with an extra move.
+// The cubic corrections below absorb a relative seed error of 2^-18, so the low word may be anything: borrow
+// the low word of a value that is dead by then, which lets the register allocator write the seed's high
+// word next to it (no move).  SDE_SEED_GARBAGE_LOW=0 restores the zero low word.
+#ifndef SDE_SEED_GARBAGE_LOW
+#define SDE_SEED_GARBAGE_LOW 1
+#endif
+#if SDE_SEED_GARBAGE_LOW
+#define SDE_SEED_LOW(seed, donor) __hiloint2double(__double2hiint(seed), __double2loint(donor))
+#else
+#define SDE_SEED_LOW(seed, donor) (seed)
+#endif
+__device__ __forceinline__ double sde_icdf_as_core_b(const double m, const double2 tc, const double base) {
     const double r = fma(m, tc.x, -1.0);
     double q = fma(r, sde_kc[0], sde_kc[1]);
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
-    const double base = *eterm + tc.y;                      // e * (-2 ln 2) - 2 ln c
     const double w2 = fma(q, r, base);                      // -2 ln w  in [1.386, 73.5]
-    // t = sqrt(w2): y0 ~ w2^-1/2, halved in the integer pipe; es = (1 - w2 y0^2)/2; t = g (1 + es + 1.5 es^2)
-    const double y0 = sde_rsqrt_approx(w2);
+    // t = sqrt(w2): y0 ~ w2^-1/2, g = w2 y0, e2 = 1 - w2 y0^2, t = g (1 + e2/2 + 3/8 e2^2)
+    const double y0 = SDE_SEED_LOW(sde_rsqrt_approx(w2), tc.x);
     const double g = w2 * y0;
-    const double yh = __hiloint2double(__double2hiint(y0) - 0x00100000, 0);          // y0 / 2 (low word of the seed is 0)
-    const double es = fma(-g, yh, 0.5);
-    const double ps = fma(es, sde_kc[8], 1.0);
-    const double t = fma(g, es * ps, g);
+    const double e2 = fma(-g, y0, 1.0);
+    const double ps = fma(e2, sde_kc[8], 0.5);
+    const double t = fma(g, e2 * ps, g);
     const double num = fma(fma(sde_kc[2], t, sde_kc[3]), t, sde_kc[4]);
     const double den = fma(fma(fma(sde_kc[5], t, sde_kc[6]), t, sde_kc[7]), t, 1.0);
-    const double r0 = sde_rcp_approx(den);
+    const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), base);
     const double ed = fma(-den, r0, 1.0);
     const double q0 = num * r0;
     const double quo = fma(q0, fma(ed, ed, ed), q0);
     return t - quo;
+}
+__device__ __forceinline__ double sde_icdf_as_core_v(const double m, const double2 tc, const double eterm) {
+    return sde_icdf_as_core_b(m, tc, eterm + tc.y);         // base = e * (-2 ln 2) - 2 ln c
+}
+__device__ __forceinline__ double sde_icdf_as_core(sde_u32 mb_hi, sde_u32 mb_lo, const double* eterm, const double* s_table_lane) {
+    const double m = __hiloint2double((int)(mb_hi | 0x3ff00000u), (int)mb_lo);       // in [1, 2)
+    // s_table_lane = s_table + (lane & 7) * 2: the copy of the log table this lane's bank group owns
+    const double2 tc = *reinterpret_cast<const double2*>(s_table_lane + (mb_hi >> 13) * (2 * SDE_ICDF_TABLE_REPL));
+    return sde_icdf_as_core_v(m, tc, *eterm);
 }
 
 // p = j * 2^-53, j a 53-bit integer (rand's f64 is (u64 >> 11) * 2^-53).  min(p, 1-p), the
@@ -136,6 +157,32 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const doub
     const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned (pos = 0 -> 0)
     double x = sde_icdf_as_core(mh >> 12, mh << 20, s_table + SDE_ICDF_LOG_DOUBLES + 20 + pos,     // h - 53 = pos - 33
                                 s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
+    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
+    return __hiloint2double(xhi, __double2loint(x));
+}
+
+// Same map with explicit 32-bit shared-window addresses (persistent kernel): `tab_lane` = address of this lane's
+// replica of log-table entry 0 of a table loaded with y_offset = SDE_ICDF_Y_OFFSET_K32.  Two integer instructions
+// per table address, and the compiler cannot rematerialise the lane-dependent part inside the step loop.
+// One shared-memory access per draw (LDS.128): the load/store data pipe is this kernel's busiest unit.
+__device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 tab_lane) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+    int pos;
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(j));
+    const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned
+    sde_u32 ta;                                              // tab_lane + (mh >> 25) * 128: shift + one multiply-add
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(mh >> 25), "r"(16u * SDE_ICDF_TABLE_REPL), "r"(tab_lane));
+    double2 tc;                                              // {1/c, -2 ln c + 194 ln 2}
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc.x), "=d"(tc.y) : "r"(ta));
+    // exponent term without a table or a conversion: D = 32 + pos/2 is exactly representable and is built by one
+    // integer multiply-add on the high word; base = D (-4 ln 2) + tc.y = -2 ln 2 (pos - 33) - 2 ln c, rounded once
+    sde_u32 dh;
+    asm("mad.lo.u32 %0, %1, 16384, 0x40400000;" : "=r"(dh) : "r"((sde_u32)pos));
+    const double base = fma(__hiloint2double((int)dh, 0), sde_kc[9], tc.y);
+    const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
+    const double x = sde_icdf_as_core_b(m, tc, base);
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
     return __hiloint2double(xhi, __double2loint(x));
 }

@@ -1,0 +1,272 @@
+// sde_sim_resident.cuh — persistent-warp variant of the fused path-simulation kernel (sm_100a).
+//
+// Same contract as sde_sim_kernel.cuh (one launch = the parallel region of sim::simulate,
+// src/sim/mod.rs:41-88; rows in the reference order of src/filtration.rs:87-113), selected by the
+// lowering for Sobol-driven full-path output [N][T][P] when everything a path reads fits in shared
+// memory for the WHOLE time grid:
+//     lane table   x_d(4 lane) ^ mask_d        S K x 32 u32   (digital shift folded in once per CTA)
+//     step records {t, t+dt, dt, sqrt dt, hoisted model constants}   S x (4 + NSLOT) f64
+//     inverse-normal tables (sde_device_icdf.cuh)
+//     per warp: x_d(n0) of the warp's current 32 paths             S K u32
+// One CTA per SM stays resident and its warps walk the work items on their own:
+//   item i = 32 paths  n = n0 + 4 lane,  n0 = n_base + 128 (i >> 2) + (i & 3)   (point index; scenario = n - 5,
+//   src/rng/sobol.rs:17), i.e. the lanes of a warp own paths 4 apart, so all 32 rows share one phase modulo a
+//   32-byte sector and every 4-step group leaves as one aligned 256-bit store per lane (st.global.v4.f64),
+//   exactly like the direct path of the tiled kernel.
+// There is no block barrier after the CTA prologue: a warp folds the Sobol part of its next item itself
+// (8 nibble-table loads per dimension, L1/L2 resident), so warps drift apart and the FP64, integer and
+// load/store phases of different warps overlap instead of marching in step; no tile prologue/epilogue code,
+// no staged prefetch registers.
+//
+// Macros expected from the generated prelude (as for sde_sim_kernel.cuh) plus
+//   SDE_S                          number of steps S = T - 1 (compile time: the plan owns the time grid)
+// Requires SDE_RNG in {2, 3} (Sobol with XOR digital shift / raw), SDE_OUT == 0, SDE_UNR == 4.
+#pragma once
+#include "sde_sim_common.cuh"
+
+#if !(SDE_RNG == 2 || SDE_RNG == 3) || SDE_OUT != 0 || SDE_UNR != 4
+#error "sde_sim_resident.cuh: Sobol (xor / raw) full-path NTP output with 4-step groups only"
+#endif
+#ifndef SDE_KK
+#define SDE_KK (SDE_K > 0 ? SDE_K : 1)
+#endif
+#ifndef SDE_NSLOT
+#define SDE_NSLOT 0
+#endif
+#ifndef SDE_ST256
+#define SDE_ST256 1
+#endif
+
+#ifndef SDE_RES_GRP
+#define SDE_RES_GRP 4                          /* steps per unrolled group: 4 or 8 (whole 32-byte sectors) */
+#endif
+#ifndef SDE_RES_PIPE
+#define SDE_RES_PIPE 1                         /* draws of group g+1 overlap the state updates of group g */
+#endif
+#define SDE_NW (SDE_BLOCK / 32)
+#define SDE_SK (SDE_S * SDE_K)
+#define SDE_STEP_LD (4 + SDE_NSLOT)
+#define SDE_BW_LD ((SDE_SK + 3) & ~3)
+#define SDE_NIB_LD ((SDE_SK + 31) & ~31)      /* leading dimension of the transposed nibble table */
+// shared-memory carve-up (bytes); mirrored by the host in lower.cpp
+#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
+#define SDE_SMEM_LANE_BYTES (SDE_SK * 32 * 4)
+#define SDE_SMEM_STEP_BYTES (SDE_S * SDE_STEP_LD * 8)
+#define SDE_SMEM_BW_BYTES (SDE_NW * SDE_BW_LD * 4)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_LANE_BYTES + SDE_SMEM_BW_BYTES)
+
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
+    extern __shared__ double4 sde_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
+    double* s_icdf = reinterpret_cast<double*>(smem);
+    double* s_step = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES);
+    sde_u32* s_lane = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_STEP_BYTES);
+    sde_u32* s_bw = s_lane + SDE_SMEM_LANE_BYTES / 4;
+    (void)s_icdf;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    constexpr int S = SDE_S, T = SDE_S + 1;
+
+    // ---- CTA prologue: the tables every path of every item reads
+#if SDE_ICDF == 1
+    sde_icdf_table_load(s_icdf, tid, SDE_BLOCK, SDE_RNG == 2 ? SDE_ICDF_Y_OFFSET_K32 : 0.0);
+#endif
+    for (int e = tid; e < SDE_SK * 32; e += SDE_BLOCK) {
+        sde_u32 v = __ldg(prm.sobol_lane + e);
+#if SDE_RNG == 2
+        v ^= __ldg(prm.xor_masks + (e >> 5));                 // u = ((x ^ mask) + 1/2) 2^-32: one mask per dimension
+#endif
+        s_lane[e] = v;
+    }
+    for (int e = tid; e < S; e += SDE_BLOCK) {
+        const double t_cur = __ldg(prm.times + e), t_next = __ldg(prm.times + e + 1);
+        const double dt = __ldg(prm.dts + e), sq = __ldg(prm.sqrt_dts + e);
+        double* rec = s_step + e * SDE_STEP_LD;
+        rec[0] = t_cur; rec[1] = t_next; rec[2] = dt; rec[3] = sq;
+#if SDE_NSLOT > 0
+        double slots[SDE_NSLOT];
+        sde_model_step_consts(t_cur, t_next, dt, sq, slots);
+#pragma unroll
+        for (int q = 0; q < SDE_NSLOT; ++q) rec[4 + q] = slots[q];
+#endif
+    }
+    __syncthreads();
+
+    sde_u32* const my_bw = s_bw + warp * SDE_BW_LD;
+    const sde_u32* const my_lane = s_lane + lane;
+#if SDE_ICDF == 1
+    const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_icdf + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
+#endif
+
+    const sde_u64 first_n = prm.scen_offset + 5ull;           // Sobol::new(..).skip(5)  (sobol.rs:17)
+    const sde_u64 n_base = first_n & ~127ull;
+    const sde_u64 n_items = 4ull * ((first_n + prm.n_paths - n_base + 127ull) >> 7);
+    const sde_u64 item_stride = (sde_u64)gridDim.x * SDE_NW;
+
+    double x0[SDE_P];
+#pragma unroll
+    for (int p = 0; p < SDE_P; ++p) x0[p] = __ldg(prm.x0 + p);
+    const double t_first = __ldg(prm.times);
+
+#pragma unroll 1
+    for (sde_u64 item = (sde_u64)blockIdx.x * SDE_NW + warp; item < n_items; item += item_stride) {
+        const sde_u64 n0 = n_base + ((item >> 2) << 7) + (item & 3ull);
+        const sde_u64 n = n0 + (sde_u64)(4 * lane);
+        const bool valid = (n >= first_n) && (n - first_n < prm.n_paths);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const long long s_local = (long long)(n - first_n);   // "negative" for the <= 5 leading pad lanes
+
+        // ---- Sobol part of this item, x_d(n0): XOR over the nibbles of gray(n0) of 16-entry tables (independent loads)
+        __syncwarp();                                         // the previous item's reads of my_bw are complete
+        {
+            // prm.sobol_nib arrives transposed for this kernel, [8][16][SDE_NIB_LD] (dimension fastest): the 32 lanes of
+            // a load read 32 consecutive dimensions of one (nibble position, nibble value) row — one 128-byte line
+            const sde_u32 g = (sde_u32)n0 ^ ((sde_u32)n0 >> 1);
+            sde_u32 off[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) off[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
+#pragma unroll 4
+            for (int d = 0; d < SDE_NIB_LD; d += 32) {
+                sde_u32 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = __ldg(prm.sobol_nib + off[q] + d);
+                if (d + lane < SDE_SK) my_bw[d + lane] = ((v[0] ^ v[1]) ^ (v[2] ^ v[3])) ^ ((v[4] ^ v[5]) ^ (v[6] ^ v[7]));
+            }
+        }
+        __syncwarp();
+
+        // ---- ScenarioFiltration::new — row 0 from initial_values, cache loaded from row 0 (filtration.rs:42-51)
+        double row[SDE_P], cache[SDE_P];
+        double ct = t_first;
+#pragma unroll
+        for (int p = 0; p < SDE_P; ++p) { row[p] = x0[p]; cache[p] = x0[p]; }
+        double* const my_row = prm.out + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's rows [T][P]
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < SDE_P; ++p) my_row[p] = row[p];
+        }
+        // step shift of this warp: the group that starts at step gamma writes elements from (gamma + 1) P on, and
+        // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
+        const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
+
+        auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+            u0 = 0.0;
+            zu[0] = 0.0;
+#pragma unroll
+            for (int k = 0; k < SDE_K; ++k) {
+                const int d = t * SDE_K + k;
+                const sde_u32 x = my_bw[d] ^ my_lane[d * 32];     // (digitally shifted) 32-bit Sobol integer
+                if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+#if SDE_RNG == 2
+                // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
+                if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1
+                    zu[k] = sde_icdf_normal_fast_k32s(x, tab_lane);
+#else
+                    zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
+#endif
+                } else {
+                    zu[k] = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+                }
+#else
+                {   // raw points: u = x / 2^32 (can be 0: the reference's ln(0) path gives NaN)
+                    const double u = (double)x * 2.3283064365386963e-10;
+                    if (k == 0) u0 = u;
+                    if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1
+                        zu[k] = sde_icdf_normal_fast(u, s_icdf, lane);
+#else
+                        zu[k] = sde_icdf_normal_reference(u);
+#endif
+                    } else {
+                        zu[k] = u;
+                    }
+                }
+#endif
+            }
+        };
+        // one step on its own (the <= 3 steps before the first and after the last aligned group)
+        auto single = [&](const int t) __attribute__((always_inline)) {
+            double zu[SDE_KK], u0;
+            draw(t, zu, u0);
+            sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
+            if (valid) {
+#pragma unroll
+                for (int p = 0; p < SDE_P; ++p) my_row[(size_t)(t + 1) * SDE_P + p] = row[p];
+            }
+        };
+
+        int t = 0;
+        const int g_eff = gamma < S ? gamma : S;
+#pragma unroll 1
+        for (; t < g_eff; ++t) single(t);
+        const int n_groups = (S - g_eff) / SDE_RES_GRP;
+        double* dst = my_row + (size_t)(g_eff + 1) * SDE_P;   // 32-byte aligned by the choice of gamma
+#ifdef SDE_DEBUG_NOSTORE
+        const int live = (valid && prm.reserved == 12345) ? 1 : 0;   // profiling aid: group stores predicated off
+#else
+        const int live = valid ? 1 : 0;
+#endif
+        // advance_group: the sequential state updates of one group (rows t+1 .. t+GRP collected in output order) and
+        // their predicated (not branched) full-sector stores: dead lanes only exist in the first and last item
+        auto advance_group = [&](const int tg, const double (&zu)[SDE_RES_GRP][SDE_KK], const double (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
+            double vals[SDE_RES_GRP * SDE_P];
+#pragma unroll
+            for (int j = 0; j < SDE_RES_GRP; ++j) {
+                sde_model_step(row, cache, ct, zu[j], u0[j], s_step + (tg + j) * SDE_STEP_LD);
+#pragma unroll
+                for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
+            }
+#pragma unroll
+            for (int q = 0; q < SDE_P * (SDE_RES_GRP / 4); ++q) {
+#if SDE_ST256
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
+                             ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
+#else
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p st.global.v2.f64 [%0], {%1, %2}; }"
+                             ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "r"(live) : "memory");
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p st.global.v2.f64 [%0], {%1, %2}; }"
+                             ::"l"(dst + 4 * q + 2), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
+#endif
+            }
+            dst += SDE_RES_GRP * SDE_P;
+        };
+#if SDE_RES_PIPE
+        // software pipeline: the state-independent uniform -> normal chains of group g+1 are issued together with the
+        // (serial) state updates of group g, so the dependent multiply chain and the stores hide behind them
+        if (n_groups > 0) {
+            double zu[SDE_RES_GRP][SDE_KK], u0[SDE_RES_GRP];
+#pragma unroll
+            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, zu[j], u0[j]);
+#pragma unroll 1
+            for (int gi = 1; gi < n_groups; ++gi, t += SDE_RES_GRP) {
+                double zn[SDE_RES_GRP][SDE_KK], un[SDE_RES_GRP];
+#pragma unroll
+                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zn[j], un[j]);
+                advance_group(t, zu, u0);
+#pragma unroll
+                for (int j = 0; j < SDE_RES_GRP; ++j) {
+                    u0[j] = un[j];
+#pragma unroll
+                    for (int k = 0; k < SDE_KK; ++k) zu[j][k] = zn[j][k];
+                }
+            }
+            advance_group(t, zu, u0);
+            t += SDE_RES_GRP;
+        }
+#else
+#pragma unroll 1
+        for (int gi = 0; gi < n_groups; ++gi, t += SDE_RES_GRP) {
+            // phase 1: the state-independent uniform -> normal chains of the group (independent instruction streams)
+            double zu[SDE_RES_GRP][SDE_KK], u0[SDE_RES_GRP];
+#pragma unroll
+            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, zu[j], u0[j]);
+            advance_group(t, zu, u0);
+        }
+#endif
+#pragma unroll 1
+        for (; t < S; ++t) single(t);
+    }
+}

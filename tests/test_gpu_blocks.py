@@ -88,6 +88,28 @@ def test_icdf_fast_mode_tolerance(oracle):
     assert err.max() <= 5e-13
 
 
+def test_icdf_fast_k32_front_end_tolerance(oracle):
+    # The digital-shift path feeds 32-bit integers k (p = (k + 1/2) 2^-32) to the integer front end, and the persistent
+    # kernel forms the exponent term arithmetically (sde_icdf_normal_fast_k32s).  Same stated tolerance: 5e-13 absolute.
+    # Every leading-one position of min(p, 1-p) (all 32 exponents, both signs), their neighbours, and random k.
+    rng = np.random.default_rng(2)
+    k = [np.uint64(0), np.uint64(2**32 - 1), np.uint64(2**31), np.uint64(2**31 - 1)]
+    for b in range(32):
+        for d in (-1, 0, 1):
+            for base in (2**b, 2**32 - 1 - 2**b):
+                v = base + d
+                if 0 <= v < 2**32:
+                    k.append(np.uint64(v))
+    k = np.concatenate([np.array(k, dtype=np.uint64), rng.integers(0, 2**32, size=400_000, dtype=np.uint64),
+                        rng.integers(0, 2**12, size=20_000, dtype=np.uint64)])          # deep left tail
+    p = (k.astype(np.float64) + 0.5) * 2.0**-32
+    ref, got = oracle.icdf_normal(p), _icdf_dev(p, 2)
+    err = np.abs(got - ref)
+    print("k32 icdf max abs err", err.max(), "at k =", int(k[np.argmax(err)]))
+    assert err.max() <= 5e-13
+    assert np.array_equal(np.signbit(got), np.signbit(ref))          # x(w) itself is slightly negative next to p = 1/2
+
+
 def test_icdf_zero_is_nan_both_modes():
     assert np.isnan(_icdf_dev([0.0], 0)[0]) and np.isnan(_icdf_dev([0.0], 1)[0])    # ln(0) path, increment.rs:165-177
 

@@ -84,7 +84,8 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
     u = S.Universe(eqs, times)
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
-                        arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"))
+                        arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"),
+                        ntp_direct=kw.get("ntp_direct", 0))
     src, nb = C.c_void_p(), C.c_size_t(0)
     rc = _ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), compile, C.byref(src), C.byref(nb))
     _ffi.check(rc)
@@ -119,6 +120,8 @@ def test_lowering_cache_rule_euler_vs_rk():
     ("C1", GBM_EQ, grid(252), "euler", "pseudo", {}),
     ("C2-xor-fast", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast"}),
     ("C2-compat", GBM_EQ, grid(252), "euler", "sobol", {}),
+    ("C2-tiled", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast", "ntp_direct": 2}),
+    ("C3-full-euler-resident", HESTON_EQ, grid(250), "euler", "sobol", {"scramble": "xor", "icdf": "fast"}),
     ("C2-tpn", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "layout": "TPN"}),
     ("C3", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor"}),
     ("C3-terminal", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal"}),
@@ -129,7 +132,9 @@ def test_lowering_cache_rule_euler_vs_rk():
 ])
 def test_configs_lower_and_compile_for_sm100a(name, eqs, times, scheme, rng, kw):
     text, nbytes = _lower(eqs, times, scheme, rng, compile=1, **kw)     # NVRTC --gpu-architecture=sm_100a, no GPU needed
-    assert '#include "sde_sim_kernel.cuh"' in text and nbytes > 10_000
+    assert ('#include "sde_sim_kernel.cuh"' in text or '#include "sde_sim_resident.cuh"' in text) and nbytes > 10_000
+    if name == "C2-xor-fast":                                           # Sobol full paths with resident tables: persistent warps
+        assert '#include "sde_sim_resident.cuh"' in text and "#define SDE_S 252" in text
 
 
 def test_joe_kuo_table_matches_scipy(oracle):

@@ -20,7 +20,10 @@ modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="refe
 which = sys.argv[1:] or ["fast"]
 out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
-grid = [("NTP", 2, tt, b, mb) for (tt, b, mb) in ((0, 256, 4), (0, 256, 3), (0, 256, 2), (64, 256, 3), (28, 256, 3))]
+grid = [("NTP", 2, 0, 256, 2), ("NTP", 2, 0, 256, 4)]
+grid += [("NTP", 3, 0, b, mb) for (b, mb) in ((1024, 0), (512, 0), (256, 0), (512, 1), (256, 2), (256, 3))]
+if os.environ.get("SWEEP_GRID"):
+    grid = [tuple(("NTP",) + tuple(int(x) for x in g.split(","))) for g in os.environ["SWEEP_GRID"].split(";")]
 for mode in which:
     for layout, direct, tt, block, mb in grid:
         try:

@@ -63,7 +63,7 @@ def _ncu_traffic_bytes():
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,power.draw.instant,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -79,16 +79,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        """Samples that arrived before this call (warm-up, nvidia-smi start-up) are not part of the timed region."""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
+        t_end = time.perf_counter()
+        t_begin = getattr(self, "t_begin", 0.0)
+        self.rows = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05]
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, pw = [], 0, set(), []
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -98,12 +105,16 @@ class ClockSampler:
                 mx = max(mx, float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None}
 
 
 def _host_threads() -> int:
@@ -187,13 +198,14 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident leg: `value`
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()                                  # nvidia-smi needs ~100 ms to produce its first sample
     for _ in range(args.warmup):
         plan.run(INIT, N, seed=SEED, scenario_offset=offset, out=out)
     barrier()
     launches0 = plan.launches
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -84,11 +84,11 @@ __constant__ double sde_kc[12] = {
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
-// 21 FP64-pipe instructions + 2 MUFU:
+// 20 FP64-pipe instructions + 2 MUFU:
 //   -2 ln w   table {1/c, -2 ln c} on the top 7 mantissa bits, r = m/c - 1 (|r| <= 2^-8), degree-3 minimax
 //             polynomial for -2 log1p(r)/r                                                               6
 //   sqrt      rsqrt.approx.f64 seed (it only sees the high word: rel ~2^-20) + one cubic step           5
-//   N/D       Horner with FMA (2 + 3), rcp.approx.f64 seed + one cubic step, t - q                      10
+//   N/D       even/odd split in w2 = t^2 (2 + 3), rcp.approx.f64 seed + one cubic step, t - N r1       9
 // Stated tolerance of the whole map against the REFERENCE evaluation: |dz| <= 5e-13 absolute.
 // The MUFU seeds only define the high word of their result; PTX zero-fills the low word with an extra move.
 // The cubic corrections below absorb a relative seed error of 2^-18, so the low word may be anything: borrow
@@ -114,13 +114,18 @@ __device__ __forceinline__ double sde_icdf_as_core_b(const double m, const doubl
     const double e2 = fma(-g, y0, 1.0);
     const double ps = fma(e2, sde_kc[8], 0.5);
     const double t = fma(g, e2 * ps, g);
-    const double num = fma(fma(sde_kc[2], t, sde_kc[3]), t, sde_kc[4]);
-    const double den = fma(fma(fma(sde_kc[5], t, sde_kc[6]), t, sde_kc[7]), t, 1.0);
+    // N(t) = (c0 + c2 w2) + c1 t and D(t) = (1 + d2 w2) + t (d1 + d3 w2): t^2 = w2 is known before the square root
+    // is, so only one FMA of each polynomial waits for t (same operation count as Horner, shorter critical path)
+    const double ne = fma(sde_kc[2], w2, sde_kc[4]);
+    const double de = fma(sde_kc[6], w2, 1.0);
+    const double dd = fma(sde_kc[5], w2, sde_kc[7]);
+    const double num = fma(sde_kc[3], t, ne);
+    const double den = fma(t, dd, de);
+    // x = t - N/D with 1/D = r0 (1 + ed + ed^2), ed = 1 - D r0 (cubic step on the MUFU seed), folded into one final FMA
     const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), base);
     const double ed = fma(-den, r0, 1.0);
-    const double q0 = num * r0;
-    const double quo = fma(q0, fma(ed, ed, ed), q0);
-    return t - quo;
+    const double r1 = fma(r0, fma(ed, ed, ed), r0);
+    return fma(-num, r1, t);
 }
 __device__ __forceinline__ double sde_icdf_as_core_v(const double m, const double2 tc, const double eterm) {
     return sde_icdf_as_core_b(m, tc, eterm + tc.y);         // base = e * (-2 ln 2) - 2 ln c

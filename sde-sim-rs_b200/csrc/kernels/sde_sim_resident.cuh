@@ -236,25 +236,31 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #if SDE_RES_PIPE
         // software pipeline: the state-independent uniform -> normal chains of group g+1 are issued together with the
         // (serial) state updates of group g, so the dependent multiply chain and the stores hide behind them
+        // (two register sets, ping-pong: no copies on the loop back edge)
         if (n_groups > 0) {
-            double zu[SDE_RES_GRP][SDE_KK], u0[SDE_RES_GRP];
+            double za[SDE_RES_GRP][SDE_KK], ua[SDE_RES_GRP], zb[SDE_RES_GRP][SDE_KK], ub[SDE_RES_GRP];
 #pragma unroll
-            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, zu[j], u0[j]);
+            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, za[j], ua[j]);
+            int left = n_groups - 1;                          // groups whose draws are still to be issued
 #pragma unroll 1
-            for (int gi = 1; gi < n_groups; ++gi, t += SDE_RES_GRP) {
-                double zn[SDE_RES_GRP][SDE_KK], un[SDE_RES_GRP];
+            for (; left >= 2; left -= 2, t += 2 * SDE_RES_GRP) {
 #pragma unroll
-                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zn[j], un[j]);
-                advance_group(t, zu, u0);
+                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zb[j], ub[j]);
+                advance_group(t, za, ua);
 #pragma unroll
-                for (int j = 0; j < SDE_RES_GRP; ++j) {
-                    u0[j] = un[j];
-#pragma unroll
-                    for (int k = 0; k < SDE_KK; ++k) zu[j][k] = zn[j][k];
-                }
+                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + 2 * SDE_RES_GRP + j, za[j], ua[j]);
+                advance_group(t + SDE_RES_GRP, zb, ub);
             }
-            advance_group(t, zu, u0);
-            t += SDE_RES_GRP;
+            if (left == 1) {
+#pragma unroll
+                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zb[j], ub[j]);
+                advance_group(t, za, ua);
+                advance_group(t + SDE_RES_GRP, zb, ub);
+                t += 2 * SDE_RES_GRP;
+            } else {
+                advance_group(t, za, ua);
+                t += SDE_RES_GRP;
+            }
         }
 #else
 #pragma unroll 1

@@ -2,6 +2,7 @@
 #include "lower.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <numeric>
 #include <sstream>
@@ -23,6 +24,9 @@ class StepGen {
     // path-independent per-step constants hoisted into the tile prologue (arithmetic=fast only):
     // each entry is a CUDA expression over t_cur, t_next, dt, sqrt_dt
     std::vector<std::string> slots;
+    // the same constants evaluated on the host, [slot][step] (IEEE fma / multiply / sqrt: bit-identical to the device),
+    // so that constants which do not change along the time grid can be emitted as literals instead of table reads
+    std::vector<std::vector<double>> slot_values;
     std::string prelude() const { return pre_.str(); }      // declarations emitted before the step body
 
     // Emits the body of sde_model_step given the cache position on entry; returns it on exit.
@@ -30,6 +34,7 @@ class StepGen {
         state_ = enter;
         o_ = &o;
         slots.clear();
+        slot_values.clear();
         pre_.str("");
         w_declared_.assign(u_.K(), false);
         {   // hoist per-step constants into the tile prologue only while the step record stays small
@@ -124,20 +129,29 @@ class StepGen {
                 // (sde_model_step_consts) and read from shared memory.  <= ~3 ulp per step vs the literal order.
                 if (state_ != CUR && !pr.terms.empty()) refresh(CUR);
                 std::string A = "1.0";
+                const int S = u_.T() - 1;
+                std::vector<double> Av(S, 1.0), dtv(S), sqv(S);
+                for (int t = 0; t < S; ++t) { dtv[t] = u_.times[t + 1] - u_.times[t]; sqv[t] = std::sqrt(dtv[t]); }
                 std::vector<double> bsum(u_.K(), 0.0);
                 std::vector<bool> bused(u_.K(), false);
                 for (size_t j = 0; j < pr.terms.size(); ++j) {
                     const Term& t = pr.terms[j];
-                    if (t.kind == IncKind::Time) A = "fma(" + format_double(lin[j]) + ", dt, " + A + ")";
-                    else if (t.kind == IncKind::Wiener) { bsum[t.factor] += lin[j]; bused[t.factor] = true; }
+                    if (t.kind == IncKind::Time) {
+                        A = "fma(" + format_double(lin[j]) + ", dt, " + A + ")";
+                        for (int q = 0; q < S; ++q) Av[q] = std::fma(lin[j], dtv[q], Av[q]);
+                    } else if (t.kind == IncKind::Wiener) { bsum[t.factor] += lin[j]; bused[t.factor] = true; }
                 }
                 if (hoist_) {
                     slots.push_back(A);
-                    line("double g = ss[" + std::to_string(3 + slots.size()) + "];");
+                    slot_values.push_back(Av);
+                    line("double g = SDE_SLOT_" + std::to_string(slots.size() - 1) + ";");
                     for (int k = 0; k < u_.K(); ++k) {
                         if (!bused[k]) continue;
                         slots.push_back("(" + format_double(bsum[k]) + " * sqrt_dt)");
-                        line("g = fma(ss[" + std::to_string(3 + slots.size()) + "], zu[" + std::to_string(k) + "], g);");
+                        std::vector<double> Bv(S);
+                        for (int q = 0; q < S; ++q) Bv[q] = bsum[k] * sqv[q];
+                        slot_values.push_back(Bv);
+                        line("g = fma(SDE_SLOT_" + std::to_string(slots.size() - 1) + ", zu[" + std::to_string(k) + "], g);");
                     }
                 } else {
                     // many (process, factor) pairs (e.g. a Cholesky-loaded basket): loadings stay immediates and the
@@ -256,7 +270,26 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     std::ostringstream body;
     StepGen gen(u, opt);
     gen.generate(L.enter_eq ? CUR : OLD, body);
-    const int nslot = (int)gen.slots.size();
+    // Per-step constants that do not move along the time grid become literals (no table read in the step loop):
+    // bit-identical values always; under arithmetic=fast also values that agree to 2^-44 relative (a uniform grid
+    // k/D gives sqrt(dt) values a few ulp apart), replaced by their median — <= 1e-13 relative in a coefficient
+    // that is multiplied by sqrt(dt) z, far inside that mode's stated <= ~3 ulp per step.
+    std::vector<std::string> slot_macro(gen.slots.size());
+    std::vector<std::string> table_slots;
+    for (size_t i = 0; i < gen.slots.size(); ++i) {
+        std::vector<double> v = gen.slot_values[i];
+        std::sort(v.begin(), v.end());
+        const double lo = v.front(), hi = v.back(), med = v[v.size() / 2];
+        const bool same = lo == hi;
+        const bool close = !opt.strict && std::isfinite(lo) && std::isfinite(hi) && (hi - lo) <= std::ldexp(std::fabs(med), -44);
+        if (same || close) {
+            slot_macro[i] = "(" + format_double(med) + ")";
+        } else {
+            slot_macro[i] = "ss[" + std::to_string(4 + table_slots.size()) + "]";
+            table_slots.push_back(gen.slots[i]);
+        }
+    }
+    const int nslot = (int)table_slots.size();
 
     // ---- launch shape
     L.block = opt.block > 0 ? opt.block : 256;
@@ -382,8 +415,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "// path-independent per-step constants, evaluated once per step in the tile prologue\n";
     s << "__device__ __forceinline__ void sde_model_step_consts(const double t_cur, const double t_next, const double dt, const double sqrt_dt, double* slots) {\n";
     s << "    (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)slots;\n";
-    for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << gen.slots[i] << ";\n";
+    for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << table_slots[i] << ";\n";
     s << "}\n";
+    for (size_t i = 0; i < slot_macro.size(); ++i) s << "#define SDE_SLOT_" << i << " " << slot_macro[i] << "\n";
     s << "__device__ __forceinline__ void sde_model_step(double (&row)[SDE_P], double (&c)[SDE_P], double& ct, const double (&zu)[SDE_KK],\n"
          "                                               const double u0, const double* __restrict__ ss) {\n";
     s << "    const double t_cur = ss[0], t_next = ss[1], dt = ss[2], sqrt_dt = ss[3];\n";

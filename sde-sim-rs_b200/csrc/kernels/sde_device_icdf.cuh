@@ -61,7 +61,14 @@ __device__ __forceinline__ double sde_rcp_approx(double a) {
 
 // y_offset is added to every -2 ln c entry: SDE_ICDF_Y_OFFSET_K32 for kernels that form the exponent term
 // arithmetically (sde_icdf_normal_fast_k32s), 0 for the ones that read it from the eln2 table.
+#ifndef SDE_ICDF_EXP_MAGIC
+#define SDE_ICDF_EXP_MAGIC 0
+#endif
+#if SDE_ICDF_EXP_MAGIC
 #define SDE_ICDF_Y_OFFSET_K32 134.47055302862938   /* 194 ln 2 = 66 ln 2 (w = 1.m 2^(pos-33)) + 128 ln 2 (D = 32 + pos/2) */
+#else
+#define SDE_ICDF_Y_OFFSET_K32 45.74771391695639    /* 66 ln 2: w = 1.m 2^(pos-33) */
+#endif
 __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, int nthreads, double y_offset = 0.0) {
     for (int i = tid; i < 128 * SDE_ICDF_TABLE_REPL; i += nthreads) {
         const int idx = i / SDE_ICDF_TABLE_REPL;
@@ -79,8 +86,9 @@ __constant__ double sde_kc[12] = {
     SDE_AS_C2, SDE_AS_C1, SDE_AS_C0,       // 2..4
     SDE_AS_D3, SDE_AS_D2, SDE_AS_D1,       // 5..7
     0.375,                                 // 8   3/8 of the cubic square-root step
-    -2.772588722239781,                    // 9   -4 ln 2: exponent term of the arithmetic variant
-    0.0, 0.0};
+    -2.772588722239781,                    // 9   -4 ln 2: exponent term, D = 32 + pos/2 variant
+    -1.3862943611198906,                   // 10  -2 ln 2: exponent term, converted-integer variant
+    0.0};
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
@@ -181,11 +189,17 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 t
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(mh >> 25), "r"(16u * SDE_ICDF_TABLE_REPL), "r"(tab_lane));
     double2 tc;                                              // {1/c, -2 ln c + 194 ln 2}
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc.x), "=d"(tc.y) : "r"(ta));
-    // exponent term without a table or a conversion: D = 32 + pos/2 is exactly representable and is built by one
-    // integer multiply-add on the high word; base = D (-4 ln 2) + tc.y = -2 ln 2 (pos - 33) - 2 ln c, rounded once
+    // exponent term without a table: base = pos (-2 ln 2) + tc.y = -2 ln 2 (pos - 33) - 2 ln c, rounded once.
+    // The int -> f64 conversion runs on the XU pipe (like FLO and the MUFU seeds), which has room; the variant
+    // SDE_ICDF_EXP_MAGIC builds D = 32 + pos/2 with an integer multiply-add on the high word instead (two integer
+    // instructions: the multiply-add and a zero low word).
+#if SDE_ICDF_EXP_MAGIC
     sde_u32 dh;
     asm("mad.lo.u32 %0, %1, 16384, 0x40400000;" : "=r"(dh) : "r"((sde_u32)pos));
     const double base = fma(__hiloint2double((int)dh, 0), sde_kc[9], tc.y);
+#else
+    const double base = fma((double)pos, sde_kc[10], tc.y);
+#endif
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double x = sde_icdf_as_core_b(m, tc, base);
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x

@@ -4,7 +4,16 @@ usage: run_variant.py N direct,block,min_blocks[,tile] [direct,block,min_blocks 
 import os
 import sys
 
+import time
+
 import torch
+
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    nv = pynvml.nvmlDeviceGetHandleByIndex(0)
+except Exception:  # noqa: BLE001
+    pynvml, nv = None, None
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sde-sim-rs_b200"))
@@ -27,6 +36,16 @@ for spec in sys.argv[2:]:
     for _ in range(runs):
         plan.run({"X1": 1.0}, N, seed=42, out=out)
     e1.record()
+    clk, pw = [], []
+    if nv is not None:                                   # launches are asynchronous: sample clocks / power while they run
+        while not e1.query():
+            clk.append(pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM))
+            pw.append(pynvml.nvmlDeviceGetPowerUsage(nv) / 1000.0)
+            time.sleep(0.005)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / runs
-    print(spec, f"{ms:.3f} ms  {N * D / ms / 1e6:.1f} G path-steps/s", flush=True)
+    extra = ""
+    if clk:
+        half = clk[len(clk) // 2:]                       # second half of the run: the power controller has settled
+        extra = f"  sm_mhz median(2nd half) {sorted(half)[len(half) // 2]}  power W mean(2nd half) {sum(pw[len(pw) // 2:]) / len(half):.0f}"
+    print(spec, f"{ms:.3f} ms  {N * D / ms / 1e6:.1f} G path-steps/s{extra}", flush=True)

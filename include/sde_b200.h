@@ -69,7 +69,9 @@ enum sde_scramble {
 };
 enum sde_icdf {
     SDE_ICDF_REFERENCE = 0, /* A&S 26.2.23 exactly as src/proc/increment.rs:161-179, IEEE log/sqrt/div, no contraction */
-    SDE_ICDF_FAST = 1       /* same formula; table-driven log + one-step Newton sqrt/div in f64; |dz| <= 5e-13 vs REFERENCE */
+    SDE_ICDF_FAST = 1,      /* same formula; table-driven log + one-step cubic sqrt/div in f64; |dz| <= 5e-13 vs REFERENCE */
+    SDE_ICDF_SINGLE = 2     /* same formula evaluated in FP32 (MUFU log2/rsqrt/rcp); |dz| <= 4e-6 vs REFERENCE — a precision
+                               tier of its own (paths stay f64), never selected implicitly                            */
 };
 enum sde_arith {
     SDE_ARITH_STRICT = 0,   /* separate mul/add roundings in the reference's evaluation order       */

@@ -68,7 +68,8 @@ PlanOptions plan_options(const Universe& u, const char* scheme, const char* rng_
         default: throw ExprError{"unknown output mode"};
     }
     if (o.layout != SDE_LAYOUT_NTP && o.layout != SDE_LAYOUT_TPN) throw ExprError{"unknown layout"};
-    po.lower.icdf = o.icdf == SDE_ICDF_FAST ? 1 : 0;
+    if (o.icdf != SDE_ICDF_REFERENCE && o.icdf != SDE_ICDF_FAST && o.icdf != SDE_ICDF_SINGLE) throw ExprError{"unknown icdf mode"};
+    po.lower.icdf = o.icdf;
     po.lower.strict = o.arith != SDE_ARITH_FAST;
     po.lower.rk_textbook = o.rk_variant == SDE_RK_TEXTBOOK;
     po.lower.block = o.block_threads;

@@ -19,7 +19,7 @@ struct LowerOptions {
     int scheme = SCHEME_EULER;
     int rng = RNG_PSEUDO;
     int out = OUT_PATHS_NTP;
-    int icdf = 0;            // 0 reference, 1 fast
+    int icdf = 0;            // 0 reference, 1 fast, 2 single (FP32 evaluation)
     bool strict = true;      // no FMA contraction in model arithmetic
     bool rk_textbook = false;
     int block = 0;           // 0 = auto

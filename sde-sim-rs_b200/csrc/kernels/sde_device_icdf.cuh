@@ -6,6 +6,7 @@
 //   REFERENCE  IEEE log / sqrt / divide and separately rounded mul/add in the reference's
 //              operation order.  Differs from the CPU oracle only by CUDA's log (<= 1 ulp)
 //              vs glibc's: |dz| <= 4 ulp(z) away from p = 0.5, <= 1e-15 absolute near it.
+//   SINGLE     FP32 evaluation (see below): a separate precision tier, |dz| <= 4e-6.
 //   FAST       table-driven log (128 x {1/c, -2 ln c}, degree-4 log1p), rsqrt.approx.f64 +
 //              one cubic step, rcp.approx.f64 + one cubic step, FMA Horner: 21 FP64-pipe
 //              instructions instead of ~60.  Stated tolerance: |dz| <= 5e-13 absolute vs
@@ -216,6 +217,38 @@ __device__ __forceinline__ double sde_icdf_normal_fast(double p, const double* s
                                 s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
     if (!(w > 0.0)) x = __longlong_as_double(0x7ff8000000000000ll);   // p = 0 -> NaN like ln(0) in the reference
     return lower ? -x : x;
+}
+
+// ---- SINGLE: the same A&S map evaluated in FP32 (icdf = "single").
+// MUFU.LG2 / MUFU.RSQ / MUFU.RCP and FP32 Horner: ~12 FP32-pipe + 3 MUFU instructions and no FP64-pipe work until the
+// conversion of the result.  Stated tolerance against the REFERENCE evaluation: |dz| <= 4e-6 absolute over the whole
+// range (<= 1e-6 for |z| <= 3; measured in tests/test_gpu_blocks.py) — two orders below A&S 26.2.23's own 4.5e-4
+// approximation error, but far above the 1e-12 of the f64 tiers: a precision tier of its own, never a default.
+__device__ __forceinline__ float sde_icdf_as_single_core(float wf) {
+    const float w2 = -1.3862943611198906f * __log2f(wf);     // -2 ln w  (w <= 1/2: |log2 w| >= 1, <= 2 ulp)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(w2));
+    const float t = w2 * y;
+    const float num = fmaf(fmaf((float)SDE_AS_C2, t, (float)SDE_AS_C1), t, (float)SDE_AS_C0);
+    const float den = fmaf(fmaf(fmaf((float)SDE_AS_D3, t, (float)SDE_AS_D2), t, (float)SDE_AS_D1), t, 1.0f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+    return fmaf(-num, r, t);
+}
+// p = (k + 1/2) 2^-32, k the 32-bit digitally shifted Sobol integer
+__device__ __forceinline__ double sde_icdf_normal_single_k32(sde_u32 k) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    const sde_u32 v = k ^ (sde_u32)sgn;                      // min(p, 1-p) = (v + 1/2) 2^-32
+    const float wf = fmaf((float)v, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float x = sde_icdf_as_single_core(wf);
+    return (double)__int_as_float(__float_as_int(x) ^ (~sgn & 0x80000000));          // p < 0.5 -> -x
+}
+// general entry: p in [0, 1); p = 0 gives NaN like the reference's ln(0) path
+__device__ __forceinline__ double sde_icdf_normal_single(double p) {
+    const bool lower = p < 0.5;
+    const float wf = (float)(lower ? p : 1.0 - p);
+    const float x = sde_icdf_as_single_core(wf);
+    return (double)(lower ? -x : x);
 }
 
 // increment.rs:182-200 verbatim.

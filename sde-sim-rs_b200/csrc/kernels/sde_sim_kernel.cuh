@@ -33,7 +33,7 @@
 //   SDE_RNG                        0 pseudo(ChaCha8)  1 sobol+per-path CP shift (reference)
 //                                  2 sobol+XOR digital shift  3 sobol raw  4 injected draws
 //   SDE_OUT                        0 paths [N][T][P]  1 paths [T][P][N]  2 terminal [N][P]  3 moments
-//   SDE_ICDF                       0 reference  1 fast
+//   SDE_ICDF                       0 reference  1 fast  2 single (FP32 evaluation)
 //   SDE_NEEDS_U0                   1 when the scheme consumes u[t][0] directly (Runge–Kutta sk)
 //   SDE_BLOCK, SDE_MIN_BLOCKS      launch bounds
 //   SDE_TT, SDE_UNR, SDE_CH        time tile, steps per unrolled group, ChaCha chunk (8 / gcd(8, K))
@@ -89,6 +89,8 @@ __device__ __forceinline__ double sde_uniform_to_draw(double u, bool wiener, con
     if (!wiener) return u;                               // Poisson factors consume the uniform itself
 #if SDE_ICDF == 1
     return sde_icdf_normal_fast(u, s_icdf, lane);
+#elif SDE_ICDF == 2
+    return sde_icdf_normal_single(u);
 #else
     return sde_icdf_normal_reference(u);
 #endif
@@ -299,6 +301,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
                     zu[k] = sde_icdf_normal_fast_j53(jc, s_icdf, lane);
+#elif SDE_ICDF == 2
+                    zu[k] = sde_icdf_normal_single((double)(long long)jc * 1.1102230246251565e-16);
 #else
                     zu[k] = sde_icdf_normal_reference((double)(long long)jc * 1.1102230246251565e-16);
 #endif
@@ -311,6 +315,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
                     zu[k] = sde_icdf_normal_fast_k32(x, s_icdf, lane);
+#elif SDE_ICDF == 2
+                    zu[k] = sde_icdf_normal_single_k32(x);
 #else
                     zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
 #endif

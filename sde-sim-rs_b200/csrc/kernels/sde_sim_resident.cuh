@@ -154,6 +154,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
             u0 = 0.0;
             zu[0] = 0.0;
+#ifdef SDE_DEBUG_NOCOMPUTE
+            zu[0] = (double)t * 1e-4;                         // profiling aid: stores only (no Sobol reads, no inverse normal)
+            return;
+#endif
 #pragma unroll
             for (int k = 0; k < SDE_K; ++k) {
                 const int d = t * SDE_K + k;
@@ -164,6 +168,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
                     zu[k] = sde_icdf_normal_fast_k32s(x, tab_lane);
+#elif SDE_ICDF == 2
+                    zu[k] = sde_icdf_normal_single_k32(x);
 #else
                     zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
 #endif
@@ -177,6 +183,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                     if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
                         zu[k] = sde_icdf_normal_fast(u, s_icdf, lane);
+#elif SDE_ICDF == 2
+                        zu[k] = sde_icdf_normal_single(u);
 #else
                         zu[k] = sde_icdf_normal_reference(u);
 #endif

@@ -48,7 +48,7 @@ extern "C" __global__ void sde_k_chacha8_u64(sde_u64 seed, sde_u64 n, sde_u64* _
 
 // K3: inverse normal CDF.  mode 0 reference evaluation, 1 fast (f64 entry), 2 fast through the 32-bit integer
 // front end of the digital-shift path with the arithmetic exponent term (sde_icdf_normal_fast_k32s): p[i] must be
-// (k + 1/2) 2^-32 for a 32-bit integer k.
+// (k + 1/2) 2^-32 for a 32-bit integer k.  mode 3 single (FP32 evaluation, f64 entry), 4 single through the 32-bit front end.
 extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal(const double* __restrict__ p, sde_u64 n, int mode, double* __restrict__ out) {
     __shared__ double4 s_raw[SDE_ICDF_TABLE_DOUBLES / 4];
     double* s_table = reinterpret_cast<double*>(s_raw);
@@ -56,6 +56,8 @@ extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal(const double
     __syncthreads();
     const sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
+    if (mode == 3) { out[i] = sde_icdf_normal_single(p[i]); return; }
+    if (mode == 4) { out[i] = sde_icdf_normal_single_k32((sde_u32)(unsigned long long)(p[i] * 4294967296.0)); return; }
     if (mode == 2) {
         const sde_u32 k = (sde_u32)(unsigned long long)(p[i] * 4294967296.0);     // exact: p 2^32 = k + 1/2, truncated
         out[i] = sde_icdf_normal_fast_k32s(k, (sde_u32)__cvta_generic_to_shared(s_table + 2 * (threadIdx.x & (SDE_ICDF_TABLE_REPL - 1))));

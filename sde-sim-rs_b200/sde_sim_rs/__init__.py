@@ -24,7 +24,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (ARITH_FAST, ARITH_STRICT, ICDF_FAST, ICDF_REFERENCE, LAYOUT_NTP, LAYOUT_TPN, OUT_MOMENTS,
+from ._ffi import (ARITH_FAST, ARITH_STRICT, ICDF_FAST, ICDF_REFERENCE, ICDF_SINGLE, LAYOUT_NTP, LAYOUT_TPN, OUT_MOMENTS,
                    OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
                    SCRAMBLE_XOR)
 
@@ -34,7 +34,7 @@ __all__ = ["simulate", "parse_equations", "Universe", "Plan", "Filtration", "sha
 _OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
 _LAYOUTS = {"NTP": LAYOUT_NTP, "TPN": LAYOUT_TPN}
 _SCRAMBLES = {"cp_shift_per_path": SCRAMBLE_CP_SHIFT_PER_PATH, "xor": SCRAMBLE_XOR, "none": SCRAMBLE_NONE}
-_ICDFS = {"reference": ICDF_REFERENCE, "fast": ICDF_FAST}
+_ICDFS = {"reference": ICDF_REFERENCE, "fast": ICDF_FAST, "single": ICDF_SINGLE}
 _ARITHS = {"strict": ARITH_STRICT, "fast": ARITH_FAST}
 _RKS = {"reference": RK_REFERENCE, "textbook": RK_TEXTBOOK}
 
@@ -298,7 +298,7 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
 
     Keyword-only extensions: `seed` (the reference draws a fresh OS-entropy seed per call,
     src/sim/mod.rs:28-29 — so does this when seed is None), `output` paths|terminal|moments, `layout`,
-    `scramble` cp_shift_per_path (reference behaviour) | xor | none, `icdf` reference|fast,
+    `scramble` cp_shift_per_path (reference behaviour) | xor | none, `icdf` reference|fast|single,
     `arithmetic` strict|fast, `rk_variant` reference|textbook, `device`, `scenario_offset`.
     """
     if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:

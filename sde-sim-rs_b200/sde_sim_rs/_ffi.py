@@ -18,7 +18,7 @@ SDE_OK, SDE_ERR_VALUE, SDE_ERR_RUNTIME = 0, 1, 2
 OUT_PATHS, OUT_TERMINAL, OUT_MOMENTS = 0, 1, 2
 LAYOUT_NTP, LAYOUT_TPN = 0, 1
 SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_XOR, SCRAMBLE_NONE = 0, 1, 2
-ICDF_REFERENCE, ICDF_FAST = 0, 1
+ICDF_REFERENCE, ICDF_FAST, ICDF_SINGLE = 0, 1, 2
 ARITH_STRICT, ARITH_FAST = 0, 1
 RK_REFERENCE, RK_TEXTBOOK = 0, 1
 

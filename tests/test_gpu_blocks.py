@@ -110,6 +110,26 @@ def test_icdf_fast_k32_front_end_tolerance(oracle):
     assert np.array_equal(np.signbit(got), np.signbit(ref))          # x(w) itself is slightly negative next to p = 1/2
 
 
+def test_icdf_single_precision_tier_tolerance(oracle):
+    # icdf="single": the A&S map in FP32.  Stated tolerance vs the reference evaluation: |dz| <= 4e-6 absolute
+    # everywhere, <= 1e-6 for |z| <= 3 (both entries: f64 uniforms and the 32-bit integer front end).
+    p = _icdf_inputs()
+    p = p[(p >= 2.0**-33) & (p <= 1 - 2.0**-33)]                       # the range a 32-bit uniform can reach
+    ref, got = oracle.icdf_normal(p), _icdf_dev(p, 3)
+    err = np.abs(got - ref)
+    print("single icdf (f64 entry) max abs err", err.max(), "central", err[np.abs(ref) <= 3].max())
+    assert err.max() <= 4e-6 and err[np.abs(ref) <= 3].max() <= 1e-6
+    rng = np.random.default_rng(3)
+    k = np.concatenate([rng.integers(0, 2**32, size=300_000, dtype=np.uint64), rng.integers(0, 2**10, size=5_000, dtype=np.uint64),
+                        np.array([0, 1, 2**31 - 1, 2**31, 2**32 - 1], dtype=np.uint64)])
+    pk = (k.astype(np.float64) + 0.5) * 2.0**-32
+    ref, got = oracle.icdf_normal(pk), _icdf_dev(pk, 4)
+    err = np.abs(got - ref)
+    print("single icdf (k32 entry) max abs err", err.max(), "central", err[np.abs(ref) <= 3].max())
+    assert err.max() <= 4e-6 and err[np.abs(ref) <= 3].max() <= 1e-6
+    assert np.isnan(_icdf_dev([0.0], 3)[0])
+
+
 def test_icdf_zero_is_nan_both_modes():
     assert np.isnan(_icdf_dev([0.0], 0)[0]) and np.isnan(_icdf_dev([0.0], 1)[0])    # ln(0) path, increment.rs:165-177
 

@@ -103,6 +103,25 @@ def test_fast_icdf_and_fma_arithmetic_tolerance(oracle):
     assert e <= 1e-11
 
 
+def test_single_precision_icdf_tier_end_to_end(oracle):
+    # f64 paths driven by FP32 normals: the path error is the icdf error propagated (sigma sqrt(dt) |dz| per step),
+    # orders above 1e-12 by construction and far below the sampling error; all three Sobol kernels must agree on it
+    times, N = grid(252), 20_000
+    ref = oracle.simulate(oracle.Universe(GBM_EQ, times), {"X1": 1.0}, N, "euler", "sobol", seed=3, scramble="xor")
+    outs = []
+    for direct in (1, 2, 3):
+        got = S.Plan(S.Universe(GBM_EQ, times), "euler", "sobol", scramble="xor", icdf="single", arithmetic="fast",
+                     ntp_direct=direct).run({"X1": 1.0}, N, seed=3).cpu().numpy()
+        outs.append(got)
+        e = rel_err(got, ref)
+        assert 1e-12 < e <= 2e-6, e
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    for rng_method in ("pseudo",):
+        ref = oracle.simulate(oracle.Universe(GBM_EQ, times), {"X1": 1.0}, 2000, "euler", rng_method, seed=3)
+        got = S.simulate(GBM_EQ, times, 2000, {"X1": 1.0}, rng_method, "euler", seed=3, icdf="single").to_numpy()
+        assert rel_err(got, ref) <= 2e-6
+
+
 def test_shard_union_is_bit_identical():
     times, init, N = grid(252, 64), {"X1": 1.0}, 5000
     for rng_method, scramble in [("sobol", "xor"), ("sobol", "cp_shift_per_path"), ("pseudo", "none")]:

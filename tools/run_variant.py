@@ -28,7 +28,7 @@ out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 for spec in sys.argv[2:]:
     f = [int(x) for x in spec.split(",")] + [0]
     plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", ntp_direct=f[0], block_threads=f[1], min_blocks=f[2],
-                  tile_steps=f[3], icdf="fast", arithmetic="fast")
+                  tile_steps=f[3], icdf=os.environ.get("ICDF", "fast"), arithmetic="fast")
     plan.run({"X1": 1.0}, N, seed=42, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -310,9 +310,10 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
         if (eligible && opt.direct != 1) {
-            // 12 warps per SM (3 per scheduler) is the measured optimum on B200: the kernel is bound by FP64-pipe and
-            // issue contention, not latency; more resident warps only add load/store-pipe queueing
-            int block = opt.block > 0 ? opt.block : 384;
+            // 8 warps per SM (2 per scheduler) is the measured optimum on B200 (profiles/r1_sweep_resident.json): the
+            // software-pipelined step loop carries its own instruction-level parallelism, the kernel is bound by FP64-pipe /
+            // issue contention and by board power, and more resident warps only add load/store-pipe queueing
+            int block = opt.block > 0 ? opt.block : 256;
             block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
             while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
             if (resident_smem(block, nslot) <= 200 * 1024) {
@@ -371,9 +372,10 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     } else {
         const int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / (L.smem_bytes + 1024));
         const int by_threads = std::max(1, 2048 / L.block);
-        const int by_regs = std::max(1, 65536 / (L.block * 64));   // the step loop wants 64 registers (no spills at 64)
-        L.min_blocks = std::max(1, std::min({by_smem, by_threads, by_regs}));
-        if (opt.min_blocks > 0) L.min_blocks = std::min(opt.min_blocks, std::min(by_smem, by_threads));
+        // one CTA per SM: its warps are the persistent workers (see the block-size note above); opt.min_blocks can ask
+        // for more resident CTAs for tuning, within what shared memory and the thread limit allow
+        L.min_blocks = 1;
+        if (opt.min_blocks > 0) L.min_blocks = std::max(1, std::min(opt.min_blocks, std::min(by_smem, by_threads)));
         L.tt = u.T() - 1;
     }
     // ---- translation unit
@@ -396,9 +398,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         if (std::getenv("SDE_B200_DEBUG_NOCOMPUTE")) s << "#define SDE_DEBUG_NOCOMPUTE 1\n";                                              // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSTORE")) s << "#define SDE_DEBUG_NOSTORE 1\n";                                                  // profiling aid
         if (const char* g = std::getenv("SDE_B200_RES_PIPE")) s << "#define SDE_RES_PIPE " << (std::atoi(g) ? 1 : 0) << "\n";          // tuning
-        // steps per unrolled group: 8 (two sector stores per lane) for one-factor one-process models, else 4
-        // (measured on B200, C2: 449 vs 440 G path-steps/s); SDE_B200_RES_GRP overrides for tuning
-        int grp = (K == 1 && P == 1 && u.T() - 1 >= 32) ? 8 : 4;
+        // steps per unrolled group: 4 (one sector store per lane per process); 8 measured equal within noise on C2
+        // (SDE_B200_RES_GRP overrides for tuning)
+        int grp = 4;
         if (const char* g = std::getenv("SDE_B200_RES_GRP")) grp = std::atoi(g) == 8 ? 8 : 4;
         s << "#define SDE_RES_GRP " << grp << "\n";
     }

@@ -1,0 +1,99 @@
+// Store-pattern ceilings for full-path output [N][T] f64 with T = 253 (row = 2024 B, not a multiple of 32 B):
+//   A  each lane owns one row and writes one aligned 32-byte sector per step group (st.global.v4.f64)  — rows 4 apart per warp
+//   B  each lane stages a 128-byte line in shared memory and hands it to the TMA (cp.async.bulk shared -> global) — rows 16 apart
+//   C  4 lanes write one 128-byte line of one row with st.global.v4.f64 (needs a transpose in a real kernel)
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o store_patterns store_patterns.cu && ./store_patterns
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int T = 253;
+
+__global__ void __launch_bounds__(1024, 1) k_sector(double* out, long long n_rows, int iters_dummy) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long n_items = n_rows / 32;
+    for (long long item = (long long)blockIdx.x * nw + warp; item < n_items; item += (long long)gridDim.x * nw) {
+        const long long s = ((item >> 2) << 7) + (item & 3) + 4 * lane;
+        double* row = out + s * T;
+        const int gamma = (int)((4 - ((s * T + 1) & 3)) & 3);
+        double v = (double)lane;
+        for (int t = gamma; t + 4 <= T - 1; t += 4) {
+            double* dst = row + t + 1;
+            v += 1.0;
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v), "d"(v), "d"(v), "d"(v) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_tma(double* out, long long n_rows, int dummy) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* stage = reinterpret_cast<double*>(smem) + (size_t)(warp * 32 + lane) * 2 * 18;   // 2 buffers x 144 B
+    const unsigned s_addr = (unsigned)__cvta_generic_to_shared(stage);
+    const long long n_items = n_rows / 32;
+    int buf = 0;
+    for (long long item = (long long)blockIdx.x * nw + warp; item < n_items; item += (long long)gridDim.x * nw) {
+        const long long s = ((item >> 4) << 9) + (item & 15) + 16 * lane;
+        const long long e0 = s * T;
+        const int phi = (int)(e0 & 15);
+        double* line = out + (e0 - phi);                       // 128-byte aligned
+        double v = (double)lane;
+        // full lines only (the partial first / last line is noise for this measurement)
+        for (int L = 1; (L + 1) * 16 <= phi + T; ++L) {
+            double* st = stage + buf * 18;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { v += 1.0; *reinterpret_cast<double2*>(st + 2 * q) = make_double2(v, v); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(line + 16 * L), "r"(s_addr + buf * 144) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            buf ^= 1;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1) k_line4(double* out, long long n_rows, int dummy) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long n_items = n_rows / 32;
+    for (long long item = (long long)blockIdx.x * nw + warp; item < n_items; item += (long long)gridDim.x * nw) {
+        // 32 rows 16 apart; instruction k writes one line of rows 8k .. 8k+7 (4 lanes per line)
+        const long long s0 = ((item >> 4) << 9) + (item & 15);
+        double v = (double)lane;
+        for (int L = 1; L < 15; ++L) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long s = s0 + 16 * (8 * k + (lane >> 2));
+                const long long e0 = s * T;
+                double* line = out + (e0 - (e0 & 15)) + 16 * L + 4 * (lane & 3);
+                v += 1.0;
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(line), "d"(v), "d"(v), "d"(v), "d"(v) : "memory");
+            }
+        }
+    }
+}
+
+int main() {
+    const long long n_rows = 1ll << 24;
+    double* out;
+    if (cudaMalloc(&out, (size_t)n_rows * T * 8 + 4096) != cudaSuccess) { printf("alloc failed\n"); return 1; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&](const char* name, auto launch, double bytes) {
+        launch(); launch();
+        cudaEventRecord(e0);
+        for (int i = 0; i < 5; ++i) launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-40s %.3f ms  %.0f GB/s  (%s)\n", name, ms / 5, bytes / (ms / 5) * 1e-6, cudaGetErrorString(cudaGetLastError()));
+    };
+    for (int threads : {128, 256, 384, 512, 768}) {
+        printf("threads/SM %d\n", threads);
+        run("A sector per lane (rows 4 apart)", [&] { k_sector<<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 62 * 32);
+        cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, threads * 288 + 128);
+        run("B TMA bulk 128 B per lane (rows 16 apart)", [&] { k_tma<<<148, threads, threads * 288 + 128>>>(out, n_rows, 0); }, (double)n_rows * 14 * 128);
+        run("C 4 lanes per 128 B line", [&] { k_line4<<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 14 * 128);
+    }
+    return 0;
+}

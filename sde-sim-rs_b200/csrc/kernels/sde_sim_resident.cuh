@@ -127,7 +127,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             sde_u32 off[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) off[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
-#pragma unroll 4
+            // all loads of up to 8 chunks (256 dimensions) in flight at once: one L2 round trip per item instead of one
+            // per pair of chunks (folding ahead inside the step loop was measured slower: it costs the loop 30 registers)
+#pragma unroll 8
             for (int d = 0; d < SDE_NIB_LD; d += 32) {
                 sde_u32 v[8];
 #pragma unroll

@@ -40,7 +40,10 @@ for spec in sys.argv[2:]:
     if nv is not None:                                   # launches are asynchronous: sample clocks / power while they run
         while not e1.query():
             clk.append(pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM))
-            pw.append(pynvml.nvmlDeviceGetPowerUsage(nv) / 1000.0)
+            try:
+                pw.append(pynvml.nvmlDeviceGetFieldValues(nv, [pynvml.NVML_FI_DEV_POWER_INSTANT])[0].value.uiVal / 1000.0)
+            except Exception:  # noqa: BLE001
+                pw.append(pynvml.nvmlDeviceGetPowerUsage(nv) / 1000.0)
             time.sleep(0.005)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / runs

@@ -396,6 +396,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";
         if (std::getenv("SDE_B200_DEBUG_NOCOMPUTE")) s << "#define SDE_DEBUG_NOCOMPUTE 1\n";                                              // profiling aid
+        if (std::getenv("SDE_B200_DEBUG_NOSCALAR")) s << "#define SDE_DEBUG_NOSCALAR 1\n";                                                // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSTORE")) s << "#define SDE_DEBUG_NOSTORE 1\n";                                                  // profiling aid
         if (const char* g = std::getenv("SDE_B200_RES_PIPE")) s << "#define SDE_RES_PIPE " << (std::atoi(g) ? 1 : 0) << "\n";          // tuning
         // steps per unrolled group: 4 (one sector store per lane per process); 8 measured equal within noise on C2

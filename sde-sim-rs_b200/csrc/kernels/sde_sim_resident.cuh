@@ -43,6 +43,13 @@
 #ifndef SDE_RES_PIPE
 #define SDE_RES_PIPE 1                         /* draws of group g+1 overlap the state updates of group g */
 #endif
+#ifndef SDE_FULL_SECTORS
+#ifdef SDE_DEBUG_NOSCALAR
+#define SDE_FULL_SECTORS 0
+#else
+#define SDE_FULL_SECTORS (SDE_P == 1 && SDE_S >= 8 && SDE_ST256)   /* row heads / tails leave as whole sectors */
+#endif
+#endif
 #define SDE_NW (SDE_BLOCK / 32)
 #define SDE_SK (SDE_S * SDE_K)
 #define SDE_STEP_LD (4 + SDE_NSLOT)
@@ -120,6 +127,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 
         // ---- Sobol part of this item, x_d(n0): XOR over the nibbles of gray(n0) of 16-entry tables (independent loads)
         __syncwarp();                                         // the previous item's reads of my_bw are complete
+#ifndef SDE_DEBUG_NOCOMPUTE
         {
             // prm.sobol_nib arrives transposed for this kernel, [8][16][SDE_NIB_LD] (dimension fastest): the 32 lanes of
             // a load read 32 consecutive dimensions of one (nibble position, nibble value) row — one 128-byte line
@@ -137,6 +145,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 if (d + lane < SDE_SK) my_bw[d + lane] = ((v[0] ^ v[1]) ^ (v[2] ^ v[3])) ^ ((v[4] ^ v[5]) ^ (v[6] ^ v[7]));
             }
         }
+#endif
         __syncwarp();
 
         // ---- ScenarioFiltration::new — row 0 from initial_values, cache loaded from row 0 (filtration.rs:42-51)
@@ -145,15 +154,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
         for (int p = 0; p < SDE_P; ++p) { row[p] = x0[p]; cache[p] = x0[p]; }
         double* const my_row = prm.out + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's rows [T][P]
-        if (valid) {
-#pragma unroll
-            for (int p = 0; p < SDE_P; ++p) my_row[p] = row[p];
-        }
         // step shift of this warp: the group that starts at step gamma writes elements from (gamma + 1) P on, and
         // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
         const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
 
-        auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+        // draw_x: uniforms -> normal / Poisson draws of step t.  `flip[k]` is XORed into the Sobol integer of factor k:
+        // zero for the lane's own path, V_d[ctz(n + 1)] for the path that follows it (x_d(n+1) = x_d(n) ^ V_d[ctz(n+1)])
+        auto draw_x = [&](const int t, const sde_u32 (&flip)[SDE_KK], double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
             u0 = 0.0;
             zu[0] = 0.0;
 #ifdef SDE_DEBUG_NOCOMPUTE
@@ -163,7 +170,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
             for (int k = 0; k < SDE_K; ++k) {
                 const int d = t * SDE_K + k;
-                const sde_u32 x = my_bw[d] ^ my_lane[d * 32];     // (digitally shifted) 32-bit Sobol integer
+                const sde_u32 x = my_bw[d] ^ my_lane[d * 32] ^ flip[k];   // (digitally shifted) 32-bit Sobol integer
                 if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
 #if SDE_RNG == 2
                 // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
@@ -197,21 +204,61 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
             }
         };
+        auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+            sde_u32 none[SDE_KK];
+#pragma unroll
+            for (int k = 0; k < SDE_KK; ++k) none[k] = 0u;
+            draw_x(t, none, zu, u0);
+        };
         // one step on its own (the <= 3 steps before the first and after the last aligned group)
         auto single = [&](const int t) __attribute__((always_inline)) {
             double zu[SDE_KK], u0;
             draw(t, zu, u0);
             sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
+#ifndef SDE_DEBUG_NOSCALAR
             if (valid) {
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) my_row[(size_t)(t + 1) * SDE_P + p] = row[p];
             }
+#endif
         };
 
         int t = 0;
         const int g_eff = gamma < S ? gamma : S;
+#if SDE_FULL_SECTORS
+        // Whole sectors only.  A row is T doubles and T is not a multiple of 4, so the 32-byte sector at a row boundary
+        // holds the last r elements of row s and the first 4 - r of row s + 1.  Written as 8-byte pieces by two lanes
+        // it costs a quarter of the kernel's store throughput (partial-sector requests; measured 460 vs 616 G
+        // path-steps/s for the store stream alone).  Instead the lane of row s writes that sector once, complete: the
+        // head of row s + 1 is x0 and at most 2 steps of path s + 1, which it recomputes from its own Sobol integers
+        // (x_d(n + 1) = x_d(n) ^ V_d[ctz(n + 1)]).  A row whose head fills a sector (gamma = 3) writes it itself; only
+        // the first row's head and the last row's tail of a launch go out as scalars.
+        double hv[4];
+        hv[0] = row[0];
+#pragma unroll 1
+        for (; t < g_eff; ++t) {
+            double zu[SDE_KK], u0;
+            draw(t, zu, u0);
+            sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
+            if (t == 0) hv[1] = row[0]; else if (t == 1) hv[2] = row[0]; else hv[3] = row[0];
+        }
+        if (gamma == 3 && g_eff == 3) {
+            const int lv = valid ? 1 : 0;
+            asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
+                         ::"l"(my_row), "d"(hv[0]), "d"(hv[1]), "d"(hv[2]), "d"(hv[3]), "r"(lv) : "memory");
+        } else if (valid && s_local == 0) {
+            for (int j = 0; j <= g_eff; ++j) my_row[j] = j == 0 ? hv[0] : (j == 1 ? hv[1] : (j == 2 ? hv[2] : hv[3]));
+        }
+#else
+#ifndef SDE_DEBUG_NOSCALAR
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < SDE_P; ++p) my_row[p] = row[p];
+        }
+#endif
 #pragma unroll 1
         for (; t < g_eff; ++t) single(t);
+#endif
         const int n_groups = (S - g_eff) / SDE_RES_GRP;
         double* dst = my_row + (size_t)(g_eff + 1) * SDE_P;   // 32-byte aligned by the choice of gamma
 #ifdef SDE_DEBUG_NOSTORE
@@ -282,7 +329,56 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             advance_group(t, zu, u0);
         }
 #endif
+#if SDE_FULL_SECTORS
+        {
+            const int r = S - t;                              // 0..3 tail elements; they start on a sector boundary
+            const int t_tail = t;
+            double tv[3];
+            tv[0] = tv[1] = tv[2] = 0.0;
+#pragma unroll 1
+            for (; t < S; ++t) {
+                double zu[SDE_KK], u0;
+                draw(t, zu, u0);
+                sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
+                if (t == t_tail) tv[0] = row[0]; else if (t == t_tail + 1) tv[1] = row[0]; else tv[2] = row[0];
+            }
+            if (r > 0) {
+                const bool has_next = valid && (sde_u64)(s_local + 1) < prm.n_paths;
+                if (__any_sync(0xffffffffu, has_next)) {
+                    // head of the next row: x0 and its first 3 - r steps (path n + 1)
+                    const sde_u32 b = (sde_u32)__ffsll((long long)(n + 1ull)) - 1u;         // ctz(n + 1)
+                    double nh[3];
+                    nh[0] = x0[0]; nh[1] = nh[2] = 0.0;
+                    double row2[SDE_P], cache2[SDE_P];
+                    double ct2 = t_first;
+                    row2[0] = x0[0]; cache2[0] = x0[0];
+#pragma unroll 1
+                    for (int j = 0; j < 3 - r; ++j) {
+                        sde_u32 flip[SDE_KK];
+#pragma unroll
+                        for (int k = 0; k < SDE_K; ++k)       // V_d[b] = nibble-table entry of the single-bit nibble value
+                            flip[k] = __ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k));
+                        double zu[SDE_KK], u0;
+                        draw_x(j, flip, zu, u0);
+                        sde_model_step(row2, cache2, ct2, zu, u0, s_step + j * SDE_STEP_LD);
+                        if (j == 0) nh[1] = row2[0]; else nh[2] = row2[0];
+                    }
+                    // sector = [tail (r), next head (4 - r)]
+                    const double o1 = r >= 2 ? tv[1] : nh[0];
+                    const double o2 = r == 3 ? tv[2] : (r == 2 ? nh[0] : nh[1]);
+                    const double o3 = r == 3 ? nh[0] : (r == 2 ? nh[1] : nh[2]);
+                    const int lv = has_next ? 1 : 0;
+                    asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
+                                 ::"l"(my_row + (t_tail + 1)), "d"(tv[0]), "d"(o1), "d"(o2), "d"(o3), "r"(lv) : "memory");
+                }
+                if (valid && !has_next) {                     // last row of the launch: nothing follows it in this buffer
+                    for (int j = 0; j < r; ++j) my_row[t_tail + 1 + j] = j == 0 ? tv[0] : (j == 1 ? tv[1] : tv[2]);
+                }
+            }
+        }
+#else
 #pragma unroll 1
         for (; t < S; ++t) single(t);
+#endif
     }
 }

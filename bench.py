@@ -88,7 +88,7 @@ class ClockSampler:
     def stop(self):
         t_end = time.perf_counter()
         t_begin = getattr(self, "t_begin", 0.0)
-        self.rows = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05]
+        rows = [r for (t, r) in list(self.rows) if t_begin <= t <= t_end + 0.05]   # the reader thread may still append
         if self.proc:
             self.proc.terminate()
             try:
@@ -96,7 +96,7 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons, pw = [], 0, set(), []
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue

@@ -310,10 +310,10 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
         if (eligible && opt.direct != 1) {
-            // 8 warps per SM (2 per scheduler) is the measured optimum on B200 (profiles/r1_sweep_resident.json): the
-            // software-pipelined step loop carries its own instruction-level parallelism, the kernel is bound by FP64-pipe /
-            // issue contention and by board power, and more resident warps only add load/store-pipe queueing
-            int block = opt.block > 0 ? opt.block : 256;
+            // 16 warps per SM (4 per scheduler), measured on B200 (profiles/r1_sweep_resident.json): the software-pipelined
+            // step loop carries its own instruction-level parallelism, and under sustained load the kernel is held by the
+            // board power limit (sw_power_cap, ~1.70-1.75 GHz), where 12-32 warps all land within 2 %
+            int block = opt.block > 0 ? opt.block : 512;
             block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
             while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
             if (resident_smem(block, nslot) <= 200 * 1024) {

@@ -20,8 +20,8 @@ modes = {"fast": dict(icdf="fast", arithmetic="fast"), "strict": dict(icdf="refe
 which = sys.argv[1:] or ["fast"]
 out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
 res = []
-grid = [("NTP", 2, 0, 256, 2), ("NTP", 2, 0, 256, 4)]
-grid += [("NTP", 3, 0, b, mb) for (b, mb) in ((1024, 0), (512, 0), (256, 0), (512, 1), (256, 2), (256, 3))]
+grid = [("NTP", 2, 0, 256, 2), ("NTP", 2, 0, 256, 4)]                     # time-tiled kernel, direct sector stores
+grid += [("NTP", 3, 0, b, 1) for b in (128, 256, 384, 512, 768, 1024)]   # persistent kernel, one CTA of b threads per SM
 if os.environ.get("SWEEP_GRID"):
     grid = [tuple(("NTP",) + tuple(int(x) for x in g.split(","))) for g in os.environ["SWEEP_GRID"].split(";")]
 for mode in which:
@@ -35,11 +35,12 @@ for mode in which:
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(5):
+            reps = int(os.environ.get("SWEEP_REPS", 40))    # long enough for the power controller to settle
+            for _ in range(reps):
                 plan.run({"X1": 1.0}, N, seed=42, out=o)
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 5
+            ms = e0.elapsed_time(e1) / reps
             r = {"mode": mode, "layout": layout, "direct": direct, "tt": tt, "block": block, "min_blocks": mb, "ms": round(ms, 4),
                  "gps": round(N * D / ms / 1e6, 1), "gbs": round(N * (D + 1) * 8 / ms / 1e6, 1)}
         except Exception as ex:  # noqa: BLE001

@@ -351,7 +351,7 @@ void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uin
 namespace {
 struct UtilModule {
     CUmodule mod = nullptr;
-    CUfunction sobol = nullptr, chacha = nullptr, icdf = nullptr, poisson = nullptr, fill = nullptr, dfma = nullptr, ffma = nullptr;
+    CUfunction sobol = nullptr, chacha = nullptr, icdf = nullptr, icdf_wide = nullptr, poisson = nullptr, fill = nullptr, dfma = nullptr, ffma = nullptr;
 };
 UtilModule& util_module(int device) {
     static std::mutex mu;
@@ -365,6 +365,8 @@ UtilModule& util_module(int device) {
         cu_check(d.cuModuleGetFunction(&m.sobol, m.mod, "sde_k_sobol_points"), "sde_k_sobol_points");
         cu_check(d.cuModuleGetFunction(&m.chacha, m.mod, "sde_k_chacha8_u64"), "sde_k_chacha8_u64");
         cu_check(d.cuModuleGetFunction(&m.icdf, m.mod, "sde_k_icdf_normal"), "sde_k_icdf_normal");
+        cu_check(d.cuModuleGetFunction(&m.icdf_wide, m.mod, "sde_k_icdf_normal_wide"), "sde_k_icdf_normal_wide");
+        cu_check(d.cuFuncSetAttribute(m.icdf_wide, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 1024 * 2 * 8 * 8), "cuFuncSetAttribute(wide)");
         cu_check(d.cuModuleGetFunction(&m.poisson, m.mod, "sde_k_icdf_poisson"), "sde_k_icdf_poisson");
         cu_check(d.cuModuleGetFunction(&m.fill, m.mod, "sde_k_fill"), "sde_k_fill");
         cu_check(d.cuModuleGetFunction(&m.dfma, m.mod, "sde_k_dfma"), "sde_k_dfma");
@@ -413,8 +415,13 @@ void util_icdf_normal(int device, int mode, const double* h_p, size_t n, double*
     din.upload(h_p, n * 8);
     uint64_t nn = n;
     CUdeviceptr pi = din.ptr(), po = dout.ptr();
-    void* args[] = {&pi, &nn, &mode, &po};
-    launch1d(m.icdf, (n + 255) / 256, 256, 0, args);
+    if (mode == 5) {                                         // 32-bit front end, 1024-entry log table
+        void* wargs[] = {&pi, &nn, &po};
+        launch1d(m.icdf_wide, std::min<uint64_t>((n + 255) / 256, 1184), 256, 1024 * 2 * 8 * 8, wargs);
+    } else {
+        void* args[] = {&pi, &nn, &mode, &po};
+        launch1d(m.icdf, (n + 255) / 256, 256, 0, args);
+    }
     cu_check(driver().cuMemcpyDtoH(h_out, dout.ptr(), n * 8), "cuMemcpyDtoH");
 }
 

@@ -303,9 +303,10 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     // Sobol-driven full paths whose tables fit in shared memory for the whole time grid: persistent warps, no time tiles
     {
         const int S = u.T() - 1;
+        bool wide = false;                                    // 1024-entry log table (128 KB): XOR digital shift only
         auto resident_smem = [&](int block, int nslot_) {     // mirrors the SDE_SMEM_* macros of sde_sim_resident.cuh
             const size_t sk = (size_t)S * K;
-            size_t icdf = (opt.icdf == 1) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;
+            size_t icdf = (opt.icdf == 1) ? (wide ? (size_t)1024 * 2 * 8 * 8 : (size_t)(128 * 2 * 8 + 64) * 8) : 0;
             return icdf + (size_t)S * (4 + nslot_) * 8 + sk * 128 + (size_t)(block / 32) * ((sk + 3) & ~(size_t)3) * 4;
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
@@ -317,6 +318,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
             block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
             while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
             if (resident_smem(block, nslot) <= 200 * 1024) {
+                wide = opt.icdf == 1 && opt.rng == RNG_SOBOL_XOR && !std::getenv("SDE_B200_NO_WIDE_TABLE");
+                if (wide && resident_smem(block, nslot) > 220 * 1024) wide = false;
+                L.icdf_wide = wide;
                 L.resident = true;
                 L.direct = true;
                 L.block = block;
@@ -395,6 +399,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";
+        if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
         if (std::getenv("SDE_B200_DEBUG_NOCOMPUTE")) s << "#define SDE_DEBUG_NOCOMPUTE 1\n";                                              // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSCALAR")) s << "#define SDE_DEBUG_NOSCALAR 1\n";                                                // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSTORE")) s << "#define SDE_DEBUG_NOSTORE 1\n";                                                  // profiling aid

@@ -89,7 +89,7 @@ __constant__ double sde_kc[12] = {
     0.375,                                 // 8   3/8 of the cubic square-root step
     -2.772588722239781,                    // 9   -4 ln 2: exponent term, D = 32 + pos/2 variant
     -1.3862943611198906,                   // 10  -2 ln 2: exponent term, converted-integer variant
-    0.0};
+    -0.6666666666666666};                  // 11  -2/3: cubic Taylor term of the wide-table logarithm
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
@@ -111,14 +111,19 @@ __constant__ double sde_kc[12] = {
 #else
 #define SDE_SEED_LOW(seed, donor) (seed)
 #endif
+// everything after the logarithm: w2 = -2 ln w  in [1.386, 73.5]  ->  x = t - N(t)/D(t), t = sqrt(w2).
+// `d1`, `d2` are dead values whose low words seed the MUFU results (see SDE_SEED_LOW).
+__device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double d1, const double d2);
 __device__ __forceinline__ double sde_icdf_as_core_b(const double m, const double2 tc, const double base) {
     const double r = fma(m, tc.x, -1.0);
     double q = fma(r, sde_kc[0], sde_kc[1]);
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
-    const double w2 = fma(q, r, base);                      // -2 ln w  in [1.386, 73.5]
+    return sde_icdf_as_tail(fma(q, r, base), tc.x, base);
+}
+__device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double d1, const double d2) {
     // t = sqrt(w2): y0 ~ w2^-1/2, g = w2 y0, e2 = 1 - w2 y0^2, t = g (1 + e2/2 + 3/8 e2^2)
-    const double y0 = SDE_SEED_LOW(sde_rsqrt_approx(w2), tc.x);
+    const double y0 = SDE_SEED_LOW(sde_rsqrt_approx(w2), d1);
     const double g = w2 * y0;
     const double e2 = fma(-g, y0, 1.0);
     const double ps = fma(e2, sde_kc[8], 0.5);
@@ -131,7 +136,7 @@ __device__ __forceinline__ double sde_icdf_as_core_b(const double m, const doubl
     const double num = fma(sde_kc[3], t, ne);
     const double den = fma(t, dd, de);
     // x = t - N/D with 1/D = r0 (1 + ed + ed^2), ed = 1 - D r0 (cubic step on the MUFU seed), folded into one final FMA
-    const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), base);
+    const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), d2);
     const double ed = fma(-den, r0, 1.0);
     const double r1 = fma(r0, fma(ed, ed, ed), r0);
     return fma(-num, r1, t);
@@ -203,6 +208,42 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 t
 #endif
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double x = sde_icdf_as_core_b(m, tc, base);
+    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
+    return __hiloint2double(xhi, __double2loint(x));
+}
+
+// ---- wide log table (persistent kernel, when shared memory allows): 1024 entries x 8 replicas = 128 KB.
+// |r| <= 2^-11 makes the cubic Taylor polynomial of -2 log1p(r) exact to r^4/2 <= 2.8e-14, one FP64 instruction less
+// than the 128-entry table's degree-3 minimax fit.  Built in the CTA prologue: invc = rn(1 / c_mid) and
+// -2 ln c = 2 ln(invc) for exactly that invc (CUDA's f64 log: <= 1 ulp), so no constant array is needed.
+#define SDE_ICDF_WIDE_BITS 10
+#define SDE_ICDF_WIDE_DOUBLES ((1 << SDE_ICDF_WIDE_BITS) * 2 * SDE_ICDF_TABLE_REPL)
+__device__ __forceinline__ void sde_icdf_wide_table_build(double* s_table, int tid, int nthreads, double y_offset) {
+    for (int i = tid; i < (1 << SDE_ICDF_WIDE_BITS) * SDE_ICDF_TABLE_REPL; i += nthreads) {
+        const int idx = i / SDE_ICDF_TABLE_REPL;
+        const double c_mid = 1.0 + ((double)idx + 0.5) * (1.0 / (double)(1 << SDE_ICDF_WIDE_BITS));
+        const double invc = __ddiv_rn(1.0, c_mid);
+        s_table[2 * i] = invc;
+        s_table[2 * i + 1] = __dadd_rn(__dmul_rn(2.0, log(invc)), y_offset);
+    }
+}
+__device__ __forceinline__ double sde_icdf_normal_fast_k32w(sde_u32 k, sde_u32 tab_lane) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+    int pos;
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(j));
+    const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned
+    sde_u32 ta;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(mh >> (32 - SDE_ICDF_WIDE_BITS)), "r"(16u * SDE_ICDF_TABLE_REPL), "r"(tab_lane));
+    double2 tc;                                              // {1/c, -2 ln c + 66 ln 2}
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc.x), "=d"(tc.y) : "r"(ta));
+    const double base = fma((double)pos, sde_kc[10], tc.y);
+    const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
+    const double r = fma(m, tc.x, -1.0);
+    double q = fma(r, sde_kc[11], 1.0);                      // -2 log1p(r) = r (-2 + r (1 - 2/3 r)) + O(r^4 / 2)
+    q = fma(q, r, -2.0);
+    const double x = sde_icdf_as_tail(fma(q, r, base), tc.x, base);
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
     return __hiloint2double(xhi, __double2loint(x));
 }

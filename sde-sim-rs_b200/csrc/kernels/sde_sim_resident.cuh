@@ -56,7 +56,10 @@
 #define SDE_BW_LD ((SDE_SK + 3) & ~3)
 #define SDE_NIB_LD ((SDE_SK + 31) & ~31)      /* leading dimension of the transposed nibble table */
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
-#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
+#ifndef SDE_ICDF_WIDE
+#define SDE_ICDF_WIDE 0                         /* 1: 1024-entry log table (128 KB), set by the lowering when it fits */
+#endif
+#define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1) ? ((SDE_ICDF_WIDE ? SDE_ICDF_WIDE_DOUBLES : SDE_ICDF_TABLE_DOUBLES) * 8) : 0)
 #define SDE_SMEM_LANE_BYTES (SDE_SK * 32 * 4)
 #define SDE_SMEM_STEP_BYTES (SDE_S * SDE_STEP_LD * 8)
 #define SDE_SMEM_BW_BYTES (SDE_NW * SDE_BW_LD * 4)
@@ -78,7 +81,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 
     // ---- CTA prologue: the tables every path of every item reads
 #if SDE_ICDF == 1
+#if SDE_ICDF_WIDE
+    sde_icdf_wide_table_build(s_icdf, tid, SDE_BLOCK, SDE_ICDF_Y_OFFSET_K32);
+#else
     sde_icdf_table_load(s_icdf, tid, SDE_BLOCK, SDE_RNG == 2 ? SDE_ICDF_Y_OFFSET_K32 : 0.0);
+#endif
 #endif
     for (int e = tid; e < SDE_SK * 32; e += SDE_BLOCK) {
         sde_u32 v = __ldg(prm.sobol_lane + e);
@@ -175,7 +182,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #if SDE_RNG == 2
                 // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
                 if (sde_factor_is_wiener(k)) {
-#if SDE_ICDF == 1
+#if SDE_ICDF == 1 && SDE_ICDF_WIDE
+                    zu[k] = sde_icdf_normal_fast_k32w(x, tab_lane);
+#elif SDE_ICDF == 1
                     zu[k] = sde_icdf_normal_fast_k32s(x, tab_lane);
 #elif SDE_ICDF == 2
                     zu[k] = sde_icdf_normal_single_k32(x);

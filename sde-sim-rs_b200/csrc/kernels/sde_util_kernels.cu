@@ -66,6 +66,17 @@ extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal(const double
     }
 }
 
+// K3w: the 32-bit front end with the 1024-entry log table of the persistent kernel (128 KB of dynamic shared memory).
+extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal_wide(const double* __restrict__ p, sde_u64 n, double* __restrict__ out) {
+    extern __shared__ double4 s_wide_raw[];
+    double* s_table = reinterpret_cast<double*>(s_wide_raw);
+    sde_icdf_wide_table_build(s_table, threadIdx.x, 256, SDE_ICDF_Y_OFFSET_K32);
+    __syncthreads();
+    const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_table + 2 * (threadIdx.x & (SDE_ICDF_TABLE_REPL - 1)));
+    for (sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (sde_u64)gridDim.x * 256)
+        out[i] = sde_icdf_normal_fast_k32w((sde_u32)(unsigned long long)(p[i] * 4294967296.0), tab_lane);
+}
+
 extern "C" __global__ void sde_k_icdf_poisson(const double* __restrict__ u, const double* __restrict__ lambda, sde_u64 n, double* __restrict__ out) {
     const sde_u64 i = (sde_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sde_icdf_poisson(u[i], lambda[i]);

@@ -434,6 +434,17 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             // full groups run unguarded (any tile length); at most SDE_UNR - 1 trailing steps take the guarded path
             const int n_groups = (t_end - t0) / SDE_UNR;
             int tc = t0;
+#if SDE_UNR == 1 && SDE_P * SDE_KK >= 256
+            // wide models (a step is thousands of instructions): ONE copy of the step in the instruction stream — a
+            // peeled last group doubles the loop's footprint past the instruction cache (64-asset basket: 2 x 105 KB,
+            // `no_instruction` was the second largest stall)
+#pragma unroll 1
+            for (int gi = 0; gi < n_groups; ++gi, tc += SDE_UNR) {
+                if (more && gi + 1 == n_groups) issue(t0 + SDE_TT, pf);
+                group(tc);
+            }
+            if (more && n_groups == 0) issue(t0 + SDE_TT, pf);
+#else
 #pragma unroll 1
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += SDE_UNR) group(tc);
             if (more) issue(t0 + SDE_TT, pf);
@@ -441,6 +452,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
             for (int j = 0; j < SDE_UNR - 1; ++j)
                 if (tc + j < t_end) single(tc + j, j);
+#endif
         }
 #endif
         if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)

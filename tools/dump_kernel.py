@@ -15,7 +15,11 @@ from sde_sim_rs import _ffi  # noqa: E402
 GBM = ["dX1 = ( 0.05 * X1 ) * dt + ( 0.1 * X1) * dW1"]
 HESTON = ["dS = ( 0.05 * S ) * dt + ( max(v, 0.0)^0.5 * S ) * dW1",
           "dv = ( 2.0 * (0.04 - v) ) * dt + ( -0.21 * max(v, 0.0)^0.5 ) * dW1 + ( 0.2142428528562855 * max(v, 0.0)^0.5 ) * dW2"]
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import basket_equations  # noqa: E402
+
 CONFIGS = {
+    "c4": (basket_equations(64)[0], 252, "euler", "sobol", dict(scramble="xor", icdf="fast", arithmetic="fast", output="moments")),
     "c2": (GBM, 252, "euler", "sobol", dict(scramble="xor", icdf="fast", arithmetic="fast")),
     "c2strict": (GBM, 252, "euler", "sobol", dict(scramble="xor", icdf="reference", arithmetic="strict")),
     "c1": (GBM, 252, "euler", "pseudo", dict()),

@@ -77,6 +77,10 @@ enum sde_arith {
     SDE_ARITH_STRICT = 0,   /* separate mul/add roundings in the reference's evaluation order       */
     SDE_ARITH_FAST = 1      /* FMA contraction allowed (differs by <= ~1 ulp per step)              */
 };
+enum sde_dtype {
+    SDE_DTYPE_F64 = 0,      /* the reference's precision (default)                                 */
+    SDE_DTYPE_F32 = 1       /* f32 variant: stated tolerance vs the f64 oracle 2e-4 relative on the tested models (tests/test_gpu_f32.py) */
+};
 enum sde_rk_variant {
     SDE_RK_REFERENCE = 0,   /* bug-compatible stale-cache semantics (src/sim/runge_kutta.rs + src/func.rs:37-39) */
     SDE_RK_TEXTBOOK = 1     /* k1 evaluated at the settled state                                    */
@@ -101,6 +105,9 @@ typedef struct sde_options {
     int32_t min_blocks;       /* 0 = auto; CTAs per SM promised to the compiler (tuning)            */
     int32_t ntp_direct;       /* SDE_LAYOUT_NTP paths: 0 = auto; 1 = shared-memory transpose; 2 = direct sector stores from the
                                * time-tiled kernel; 3 = persistent-warp kernel with resident tables (Sobol xor / none only)        */
+    int32_t dtype;            /* enum sde_dtype: element type of the state, the model arithmetic and the stored rows.
+                               * SDE_DTYPE_F32 needs arith = SDE_ARITH_FAST; paths / terminal buffers are then float,
+                               * moments stay [P][3] f64 (accumulated in f64 from the f32 terminal values)                        */
 } sde_options;
 
 void sde_options_default(sde_options* o);
@@ -119,7 +126,7 @@ void sde_plan_free(sde_plan* p);
 const char* sde_plan_source(const sde_plan* p);
 /* 0/1: was the cubin found in the ahead-of-time table instead of being NVRTC-compiled? */
 int sde_plan_is_prelowered(const sde_plan* p);
-/* Number of f64 elements a run over N scenarios writes for the plan's output mode. */
+/* Number of elements (f64, or f32 for SDE_DTYPE_F32 paths / terminal values) a run over N scenarios writes. */
 size_t sde_plan_output_elems(const sde_plan* p, uint64_t n_scenarios);
 
 /* Lowering without a device (works on a CPU-only machine; used by the build check and tests):

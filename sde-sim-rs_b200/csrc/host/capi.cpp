@@ -72,6 +72,8 @@ PlanOptions plan_options(const Universe& u, const char* scheme, const char* rng_
     po.lower.icdf = o.icdf;
     po.lower.strict = o.arith != SDE_ARITH_FAST;
     po.lower.rk_textbook = o.rk_variant == SDE_RK_TEXTBOOK;
+    if (o.dtype != SDE_DTYPE_F64 && o.dtype != SDE_DTYPE_F32) throw ExprError{"unknown dtype"};
+    po.lower.f32 = o.dtype == SDE_DTYPE_F32;
     po.lower.block = o.block_threads;
     po.lower.tile_steps = o.tile_steps;
     po.lower.min_blocks = o.min_blocks;
@@ -104,6 +106,7 @@ void sde_options_default(sde_options* o) {
     o->icdf = SDE_ICDF_REFERENCE;
     o->arith = SDE_ARITH_STRICT;
     o->rk_variant = SDE_RK_REFERENCE;
+    o->dtype = SDE_DTYPE_F64;
 }
 
 int sde_universe_parse(const char* const* equations, size_t n_equations, const double* times, size_t n_times, sde_universe** out) {
@@ -199,7 +202,7 @@ int sde_simulate(const sde_universe* u, const char* const* init_names, const dou
         r->n = n_scenarios;
         r->elems = r->plan->output_elems(n_scenarios);
         use_device(po.device);
-        r->values.alloc(r->elems * 8);
+        r->values.alloc(r->plan->output_bytes(n_scenarios));
         r->plan->run_device(init_pairs(init_names, init_vals, n_init), n_scenarios, o.seed, o.scenario_offset,
                             r->values.as<double>(), o.inject, nullptr, nullptr);
         r->kernel_ms = r->plan->last_kernel_ms();
@@ -224,7 +227,7 @@ int sde_result_values_host(const sde_result* r, double* dst, size_t n_elems) {
         if (!r || !dst) throw ExprError{"NULL argument"};
         if (n_elems < r->elems) throw ExprError{"destination too small"};
         use_device(r->plan->device());
-        cu_check(driver().cuMemcpyDtoH(dst, r->values.ptr(), r->elems * 8), "cuMemcpyDtoH");
+        cu_check(driver().cuMemcpyDtoH(dst, r->values.ptr(), r->plan->output_bytes(r->n)), "cuMemcpyDtoH");
     });
 }
 double sde_result_kernel_ms(const sde_result* r) { return r ? r->kernel_ms : 0.0; }

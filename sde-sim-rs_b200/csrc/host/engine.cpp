@@ -311,7 +311,7 @@ void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uin
     const int out = opt_.lower.out;
     if (out == OUT_MOMENTS || out == OUT_PATHS_TPN) {
         // single shot: moments are tiny; the transposed layout is not scenario-contiguous
-        size_t bytes = output_elems(n) * 8;
+        size_t bytes = output_elems(n) * (out == OUT_MOMENTS ? 8 : elem_bytes());
         DeviceBuffer tmp(bytes);
         launch(n, seed, scenario_offset, tmp.as<double>(), nullptr, own_stream_, n_launches);
         cu_check(d.cuMemcpyDtoHAsync(h_out, tmp.ptr(), bytes, own_stream_), "cuMemcpyDtoHAsync");
@@ -321,10 +321,11 @@ void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uin
     // scenario-chunked, double-buffered: chunk i simulates while chunk i-1 drains over PCIe
     const size_t row_elems = out == OUT_TERMINAL ? (size_t)u_.P() : (size_t)u_.T() * u_.P();
     const size_t target_bytes = (size_t)512 << 20;
-    uint64_t chunk = std::max<uint64_t>(1, target_bytes / (row_elems * 8));
+    const size_t eb = elem_bytes();
+    uint64_t chunk = std::max<uint64_t>(1, target_bytes / (row_elems * eb));
     chunk = std::min<uint64_t>(n, std::max<uint64_t>(chunk, (uint64_t)low_.block));
     for (int b = 0; b < 2; ++b)
-        if (d_chunk_[b].bytes() < chunk * row_elems * 8) d_chunk_[b].alloc(chunk * row_elems * 8);
+        if (d_chunk_[b].bytes() < chunk * row_elems * eb) d_chunk_[b].alloc(chunk * row_elems * eb);
     uint64_t done = 0;
     int i = 0;
     bool used[2] = {false, false};
@@ -335,7 +336,7 @@ void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uin
         launch(m, seed, scenario_offset + done, d_chunk_[b].as<double>(), nullptr, own_stream_, n_launches);
         cu_check(d.cuEventRecord(ev_done_[b], own_stream_), "cuEventRecord");
         cu_check(d.cuStreamWaitEvent(copy_stream_, ev_done_[b], 0), "cuStreamWaitEvent");
-        cu_check(d.cuMemcpyDtoHAsync(h_out + done * row_elems, d_chunk_[b].ptr(), m * row_elems * 8, copy_stream_), "cuMemcpyDtoHAsync");
+        cu_check(d.cuMemcpyDtoHAsync(reinterpret_cast<unsigned char*>(h_out) + done * row_elems * eb, d_chunk_[b].ptr(), m * row_elems * eb, copy_stream_), "cuMemcpyDtoHAsync");
         cu_check(d.cuEventRecord(ev_copied_[b], copy_stream_), "cuEventRecord");
         used[b] = true;
         done += m;

@@ -39,6 +39,9 @@ class Plan {
     const PlanOptions& options() const { return opt_; }
     bool prelowered() const { return prelowered_; }
     size_t output_elems(uint64_t n) const;
+    // bytes per element of paths / terminal output (moments are always f64)
+    size_t elem_bytes() const { return opt_.lower.f32 ? 4 : 8; }
+    size_t output_bytes(uint64_t n) const { return output_elems(n) * (opt_.lower.out == OUT_MOMENTS ? 8 : elem_bytes()); }
 
     // Asynchronous on `stream` (nullptr = the plan's own stream, then synchronised before return).
     void run_device(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,

@@ -20,6 +20,23 @@ std::string format_double(double v) {
 }
 
 namespace {
+thread_local bool g_real_f32 = false;
+}
+void set_real_literals_f32(bool f32) { g_real_f32 = f32; }
+bool real_literals_f32() { return g_real_f32; }
+std::string format_real(double v) {
+    if (!g_real_f32) return format_double(v);
+    const float f = (float)v;
+    if (std::isnan(f)) return "__int_as_float(0x7fc00000)";
+    if (std::isinf(f)) return f > 0 ? "__int_as_float(0x7f800000)" : "__int_as_float(0xff800000)";
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.9g", (double)f);
+    std::string s(buf);
+    if (s.find_first_of(".eE") == std::string::npos) s += ".0";
+    return s + "f";
+}
+
+namespace {
 
 struct BinOpInfo { const char* tok; Op op; int level; bool word; };
 // fasteval gives every binary operator its own precedence (enum order), except that the six
@@ -205,7 +222,7 @@ std::string Expr::emit_node(int i, bool strict, const std::string& c, const std:
         return strict ? std::string(strict_fn) + "(" + A(0) + ", " + A(1) + ")" : "(" + A(0) + " " + op + " " + A(1) + ")";
     };
     switch (n.op) {
-        case Op::Const: { std::string s = format_double(n.value); return n.value < 0 || std::signbit(n.value) ? "(" + s + ")" : s; }
+        case Op::Const: { std::string s = format_real(n.value); return n.value < 0 || std::signbit(n.value) ? "(" + s + ")" : s; }
         case Op::Time: return t;
         case Op::Var: return c + "[" + std::to_string(n.var) + "]";
         case Op::Neg: return "(-" + A(0) + ")";
@@ -222,10 +239,10 @@ std::string Expr::emit_node(int i, bool strict, const std::string& c, const std:
             if (ex.op == Op::Const && ex.value == 1.0) return A(0);
             return "pow(" + A(0) + ", " + A(1) + ")";
         }
-        case Op::Lt: return "((" + A(0) + " < " + A(1) + ") ? 1.0 : 0.0)";
-        case Op::Gt: return "((" + A(0) + " > " + A(1) + ") ? 1.0 : 0.0)";
-        case Op::Le: return "((" + A(0) + " <= " + A(1) + ") ? 1.0 : 0.0)";
-        case Op::Ge: return "((" + A(0) + " >= " + A(1) + ") ? 1.0 : 0.0)";
+        case Op::Lt: return "((" + A(0) + " < " + A(1) + ") ? " + format_real(1.0) + " : " + format_real(0.0) + ")";
+        case Op::Gt: return "((" + A(0) + " > " + A(1) + ") ? " + format_real(1.0) + " : " + format_real(0.0) + ")";
+        case Op::Le: return "((" + A(0) + " <= " + A(1) + ") ? " + format_real(1.0) + " : " + format_real(0.0) + ")";
+        case Op::Ge: return "((" + A(0) + " >= " + A(1) + ") ? " + format_real(1.0) + " : " + format_real(0.0) + ")";
         case Op::Eq: return "sde_f_eq(" + A(0) + ", " + A(1) + ")";
         case Op::Ne: return "sde_f_ne(" + A(0) + ", " + A(1) + ")";
         case Op::And: return "sde_f_and(" + A(0) + ", " + A(1) + ")";
@@ -235,14 +252,16 @@ std::string Expr::emit_node(int i, bool strict, const std::string& c, const std:
             if (f == "int") return "trunc(" + A(0) + ")";
             if (f == "abs") return "fabs(" + A(0) + ")";
             if (f == "sign") return "sde_f_sign(" + A(0) + ")";
-            if (f == "e") return "2.718281828459045";
-            if (f == "pi") return "3.141592653589793";
+            if (f == "e") return format_real(2.718281828459045);
+            if (f == "pi") return format_real(3.141592653589793);
             if (f == "log") {
                 if (n.args.size() == 1) return "log10(" + A(0) + ")";
+                if (real_literals_f32()) return "(log(" + A(1) + ") / log(" + A(0) + "))";
                 return "__ddiv_rn(log(" + A(1) + "), log(" + A(0) + "))";       // log(base, x) = ln x / ln base
             }
             if (f == "round") {
                 if (n.args.size() == 1) return "round(" + A(0) + ")";
+                if (real_literals_f32()) return "(round(" + A(1) + " / " + A(0) + ") * " + A(0) + ")";
                 return "__dmul_rn(round(__ddiv_rn(" + A(1) + ", " + A(0) + ")), " + A(0) + ")";
             }
             if (f == "min" || f == "max") {

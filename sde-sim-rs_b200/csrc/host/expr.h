@@ -52,5 +52,11 @@ class Expr {
 };
 
 std::string format_double(double v);   // shortest round-trip literal usable in CUDA source
+// Literals of the generated MODEL code: f64 as format_double; in f32 mode (dtype f32 plans) single-precision
+// literals ("0.05f"), so that no double arithmetic sneaks into a float model.  The mode is thread-local and is
+// set by lower_model for the duration of one lowering.
+std::string format_real(double v);
+void set_real_literals_f32(bool f32);
+bool real_literals_f32();
 
 }  // namespace sde

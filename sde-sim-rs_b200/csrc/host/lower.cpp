@@ -54,7 +54,7 @@ class StepGen {
             hoist_ = n <= 16;
         }
         const int P = u_.P();
-        for (int p = 0; p < P; ++p) line("double n" + std::to_string(p) + " = 0.0;");   // row t+1 is zero until set (filtration.rs:28)
+        for (int p = 0; p < P; ++p) line("sde_real n" + std::to_string(p) + " = " + format_real(0.0) + ";");   // row t+1 is zero until set (filtration.rs:28)
         if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
         for (int p = 0; p < P; ++p) line("row[" + std::to_string(p) + "] = n" + std::to_string(p) + ";");
         return state_;
@@ -130,7 +130,7 @@ class StepGen {
                 // A and B_k do not depend on the path: they are computed once per step in the tile prologue
                 // (sde_model_step_consts) and read from shared memory.  <= ~3 ulp per step vs the literal order.
                 if (state_ != CUR && !pr.terms.empty()) refresh(CUR);
-                std::string A = "1.0";
+                std::string A = format_real(1.0);
                 const int S = u_.T() - 1;
                 std::vector<double> Av(S, 1.0), dtv(S), sqv(S);
                 for (int t = 0; t < S; ++t) { dtv[t] = u_.times[t + 1] - u_.times[t]; sqv[t] = std::sqrt(dtv[t]); }
@@ -139,17 +139,17 @@ class StepGen {
                 for (size_t j = 0; j < pr.terms.size(); ++j) {
                     const Term& t = pr.terms[j];
                     if (t.kind == IncKind::Time) {
-                        A = "fma(" + format_double(lin[j]) + ", dt, " + A + ")";
+                        A = "fma(" + format_real(lin[j]) + ", dt, " + A + ")";
                         for (int q = 0; q < S; ++q) Av[q] = std::fma(lin[j], dtv[q], Av[q]);
                     } else if (t.kind == IncKind::Wiener) { bsum[t.factor] += lin[j]; bused[t.factor] = true; }
                 }
                 if (hoist_) {
                     slots.push_back(A);
                     slot_values.push_back(Av);
-                    line("double g = SDE_SLOT_" + std::to_string(slots.size() - 1) + ";");
+                    line("sde_real g = SDE_SLOT_" + std::to_string(slots.size() - 1) + ";");
                     for (int k = 0; k < u_.K(); ++k) {
                         if (!bused[k]) continue;
-                        slots.push_back("(" + format_double(bsum[k]) + " * sqrt_dt)");
+                        slots.push_back("(" + format_real(bsum[k]) + " * sqrt_dt)");
                         std::vector<double> Bv(S);
                         for (int q = 0; q < S; ++q) Bv[q] = bsum[k] * sqv[q];
                         slot_values.push_back(Bv);
@@ -158,10 +158,10 @@ class StepGen {
                 } else {
                     // many (process, factor) pairs (e.g. a Cholesky-loaded basket): loadings stay immediates and the
                     // scaled draws w_k = sqrt(dt) z_k are shared by all processes
-                    line("double g = " + A + ";");
+                    line("sde_real g = " + A + ";");
                     for (int k = 0; k < u_.K(); ++k) {
                         if (!bused[k]) continue;
-                        if (!w_declared_[k]) { pre_ << "    const double w" << k << " = sqrt_dt * zu[" << k << "];\n"; w_declared_[k] = true; }
+                        if (!w_declared_[k]) { pre_ << "    const sde_real w" << k << " = sqrt_dt * zu[" << k << "];\n"; w_declared_[k] = true; }
                         // loadings live in constant memory: DFMA reads c[bank][offset] operands directly, whereas a 64-bit
                         // literal costs two uniform moves per use (measured on the 64-asset basket: 8 339 UMOV for 6 500 DFMA)
                         model_consts.push_back(bsum[k]);
@@ -171,17 +171,17 @@ class StepGen {
                 for (size_t j = 0; j < pr.terms.size(); ++j) {
                     if (pr.terms[j].kind != IncKind::Poisson) continue;
                     std::string x = increment(pr.terms[j]);
-                    line("g = fma(" + format_double(lin[j]) + ", " + x + ", g);");
+                    line("g = fma(" + format_real(lin[j]) + ", " + x + ", g);");
                 }
                 line("n" + sp + " = row[" + sp + "] * g; }");   // Levy slots of the cache always equal row t in Euler
                 continue;
             }
-            line("double val = row[" + sp + "];");
+            line("sde_real val = row[" + sp + "];");
             for (const Term& t : pr.terms) {
                 std::string cf = eval(t.coeff, CUR);
-                line("{ const double cf = " + cf + ";");
+                line("{ const sde_real cf = " + cf + ";");
                 std::string x = increment(t);
-                line("  const double x = " + x + ";");
+                line("  const sde_real x = " + x + ";");
                 line("  val = " + add("val", mul("cf", "x")) + "; }");
             }
             line("n" + sp + " = val; }");
@@ -194,22 +194,22 @@ class StepGen {
 
     void runge_kutta() {                                     // src/sim/runge_kutta.rs:5-107
         const int P = u_.P();
-        line("const double sk = (u0 > 0.5) ? 1.0 : -1.0;   // runge_kutta.rs:18-22");
+        line("const sde_real sk = (u0 > " + format_real(0.5) + ") ? " + format_real(1.0) + " : " + format_real(-1.0) + ";   // runge_kutta.rs:18-22");
         if (opt_.rk_textbook) state_ = OLD;                  // textbook variant: k1 at the settled row
         for (int p = 0; p < P; ++p) {                        // :26-35 pre-sample, reused by k1 and k2
             const Process& pr = u_.processes[p];
             if (!pr.levy) continue;
             for (size_t j = 0; j < pr.terms.size(); ++j) {
                 std::string x = increment(pr.terms[j]);
-                line("const double inc_" + std::to_string(p) + "_" + std::to_string(j) + " = " + x + ";");
+                line("const sde_real inc_" + std::to_string(p) + "_" + std::to_string(j) + " = " + x + ";");
             }
         }
-        for (int p = 0; p < P; ++p) line("const double x" + std::to_string(p) + " = row[" + std::to_string(p) + "];");   // :38-42
+        for (int p = 0; p < P; ++p) line("const sde_real x" + std::to_string(p) + " = row[" + std::to_string(p) + "];");   // :38-42
         for (int p = 0; p < P; ++p) {                        // :45-55  k1
             const Process& pr = u_.processes[p];
             if (!pr.levy) continue;
             std::string k = "k1_" + std::to_string(p);
-            line("double " + k + " = 0.0;");
+            line("sde_real " + k + " = " + format_real(0.0) + ";");
             for (size_t j = 0; j < pr.terms.size(); ++j) {
                 std::string cf = eval(pr.terms[j].coeff, CUR);
                 line(k + " = " + add(k, mul(cf, "inc_" + std::to_string(p) + "_" + std::to_string(j))) + ";");
@@ -219,7 +219,7 @@ class StepGen {
             const Process& pr = u_.processes[p];
             if (!pr.levy) continue;
             std::string sp = std::to_string(p);
-            line("{ double pert = 0.0;");
+            line("{ sde_real pert = " + format_real(0.0) + ";");
             for (const Term& t : pr.terms) {
                 if (t.kind != IncKind::Wiener) continue;
                 std::string cf = eval(t.coeff, CUR);
@@ -231,7 +231,7 @@ class StepGen {
             const Process& pr = u_.processes[p];
             if (!pr.levy) continue;
             std::string k = "k2_" + std::to_string(p);
-            line("double " + k + " = 0.0;");
+            line("sde_real " + k + " = " + format_real(0.0) + ";");
             for (size_t j = 0; j < pr.terms.size(); ++j) {
                 std::string cf = eval(pr.terms[j].coeff, NEXT);
                 line(k + " = " + add(k, mul(cf, "inc_" + std::to_string(p) + "_" + std::to_string(j))) + ";");
@@ -239,7 +239,7 @@ class StepGen {
         }
         for (int p : u_.levy_indices) {                      // :94-97
             std::string sp = std::to_string(p);
-            line("n" + sp + " = " + add("x" + sp, mul("0.5", add("k1_" + sp, "k2_" + sp))) + ";");
+            line("n" + sp + " = " + add("x" + sp, mul(format_real(0.5), add("k1_" + sp, "k2_" + sp))) + ";");
         }
         if (opt_.rk_textbook && !u_.algebraic_indices.empty()) state_ = OLD;
         for (int a : u_.algebraic_indices) {                 // :101-106 (sees the probe row: cache not refreshed)
@@ -253,8 +253,18 @@ int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 }  // namespace
 
+namespace {
+struct RealLiteralMode {                                     // format_real() follows the plan's dtype while it is lowered
+    explicit RealLiteralMode(bool f32) { set_real_literals_f32(f32); }
+    ~RealLiteralMode() { set_real_literals_f32(false); }
+};
+}  // namespace
+
 Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     const int P = u.P(), K = u.K();
+    if (opt.f32 && opt.strict)
+        throw ExprError{"dtype f32 needs arithmetic=\"fast\" (strict reproduces the reference's f64 operation order)"};
+    RealLiteralMode literal_mode(opt.f32);
     if (P == 0) throw ExprError{"no equations"};
     if (u.T() < 2) throw ExprError{"time_steps needs at least two points"};
     if (opt.scheme == SCHEME_RK && K == 0)
@@ -288,9 +298,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         const bool same = lo == hi;
         const bool close = !opt.strict && std::isfinite(lo) && std::isfinite(hi) && (hi - lo) <= std::ldexp(std::fabs(med), -44);
         if (same || close) {
-            slot_macro[i] = "(" + format_double(med) + ")";
+            slot_macro[i] = "(" + format_real(med) + ")";
         } else {
-            slot_macro[i] = "ss[" + std::to_string(4 + table_slots.size()) + "]";
+            slot_macro[i] = "((sde_real)ss[" + std::to_string(4 + table_slots.size()) + "])";
             table_slots.push_back(gen.slots[i]);
         }
     }
@@ -303,7 +313,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
     // full paths in reference order: straight from registers as aligned 256-bit stores when a group is 4 steps
     // and no ChaCha block alignment ties groups to the time origin; otherwise through the shared-memory transpose
-    const bool sector_stores_ok = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && P <= 8 && opt.direct != 0;
+    const bool sector_stores_ok = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && P <= 8 && opt.direct != 0 && !opt.f32;
     L.direct = sector_stores_ok && (L.block % 128) == 0;
     // Sobol-driven full paths whose tables fit in shared memory for the whole time grid: persistent warps, no time tiles
     {
@@ -358,7 +368,8 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
-        size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * 8 : 0;
+        size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * (opt.f32 ? 4 : 8) : 0;
+        tile = (tile + 7) & ~(size_t)7;
         size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
         return icdf + tile + 2 * stage + mom;
@@ -399,6 +410,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     }
     s << "#define SDE_P " << P << "\n#define SDE_K " << K << "\n#define SDE_KK " << KK << "\n";
     s << "#define SDE_SCHEME " << opt.scheme << "\n#define SDE_RNG " << opt.rng << "\n#define SDE_OUT " << opt.out << "\n";
+    if (opt.f32) s << "#define SDE_F32 1\n";
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
@@ -432,14 +444,14 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << table_slots[i] << ";\n";
     s << "}\n";
     if (!gen.model_consts.empty()) {
-        s << "__constant__ double sde_mc[" << gen.model_consts.size() << "] = {";
-        for (size_t i = 0; i < gen.model_consts.size(); ++i) s << (i ? ", " : "") << format_double(gen.model_consts[i]);
+        s << "__constant__ sde_real sde_mc[" << gen.model_consts.size() << "] = {";
+        for (size_t i = 0; i < gen.model_consts.size(); ++i) s << (i ? ", " : "") << format_real(gen.model_consts[i]);
         s << "};\n";
     }
     for (size_t i = 0; i < slot_macro.size(); ++i) s << "#define SDE_SLOT_" << i << " " << slot_macro[i] << "\n";
-    s << "__device__ __forceinline__ void sde_model_step(double (&row)[SDE_P], double (&c)[SDE_P], double& ct, const double (&zu)[SDE_KK],\n"
-         "                                               const double u0, const double* __restrict__ ss) {\n";
-    s << "    const double t_cur = ss[0], t_next = ss[1], dt = ss[2], sqrt_dt = ss[3];\n";
+    s << "__device__ __forceinline__ void sde_model_step(sde_real (&row)[SDE_P], sde_real (&c)[SDE_P], double& ct, const sde_real (&zu)[SDE_KK],\n"
+         "                                               const sde_real u0, const double* __restrict__ ss) {\n";
+    s << "    const sde_real t_cur = (sde_real)ss[0], t_next = (sde_real)ss[1], dt = (sde_real)ss[2], sqrt_dt = (sde_real)ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
     s << gen.prelude() << body.str();
     s << "}\n#include \"" << (L.resident ? "sde_sim_resident.cuh" : "sde_sim_kernel.cuh") << "\"\n";

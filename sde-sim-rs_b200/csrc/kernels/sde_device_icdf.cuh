@@ -277,19 +277,19 @@ __device__ __forceinline__ float sde_icdf_as_single_core(float wf) {
     return fmaf(-num, r, t);
 }
 // p = (k + 1/2) 2^-32, k the 32-bit digitally shifted Sobol integer
-__device__ __forceinline__ double sde_icdf_normal_single_k32(sde_u32 k) {
+__device__ __forceinline__ float sde_icdf_normal_single_k32(sde_u32 k) {   // float: f64 plans widen it, f32 plans use it as is
     const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
     const sde_u32 v = k ^ (sde_u32)sgn;                      // min(p, 1-p) = (v + 1/2) 2^-32
     const float wf = fmaf((float)v, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float x = sde_icdf_as_single_core(wf);
-    return (double)__int_as_float(__float_as_int(x) ^ (~sgn & 0x80000000));          // p < 0.5 -> -x
+    return __int_as_float(__float_as_int(x) ^ (~sgn & 0x80000000));                  // p < 0.5 -> -x
 }
 // general entry: p in [0, 1); p = 0 gives NaN like the reference's ln(0) path
-__device__ __forceinline__ double sde_icdf_normal_single(double p) {
+__device__ __forceinline__ float sde_icdf_normal_single(double p) {
     const bool lower = p < 0.5;
     const float wf = (float)(lower ? p : 1.0 - p);
     const float x = sde_icdf_as_single_core(wf);
-    return (double)(lower ? -x : x);
+    return lower ? -x : x;
 }
 
 // increment.rs:182-200 verbatim.

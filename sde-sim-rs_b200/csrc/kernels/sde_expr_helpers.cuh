@@ -3,7 +3,20 @@
 // src/func.rs:18-42 ([3P-unverified]).
 #pragma once
 
+// sde_real: the type of the model state, the draws and the output rows — double, or float for dtype = f32 plans
+// (the f32 variant: state, arithmetic and stored rows in single precision; time-grid quantities stay f64 on the host
+// and are rounded once when a step reads them).
+#ifndef SDE_F32
+#define SDE_F32 0
+#endif
+#if SDE_F32
+typedef float sde_real;
+#else
+typedef double sde_real;
+#endif
+
 #define SDE_F_EPS8 1.7763568394002505e-15   /* 8 * f64::EPSILON: fasteval's f64_eq! tolerance */
+#define SDE_F_EPS8F 9.5367431640625e-7f     /* 8 * f32::EPSILON: the same rule for the f32 variant */
 
 __device__ __forceinline__ double sde_f_sq(double x) { return __dmul_rn(x, x); }
 __device__ __forceinline__ double sde_f_nan() { return __longlong_as_double(0x7ff8000000000000ll); }
@@ -18,3 +31,16 @@ __device__ __forceinline__ double sde_f_sign(double x) { return (x != x) ? x : (
 // NaN-propagating min/max folded left to right
 __device__ __forceinline__ double sde_f_min(double a, double b) { return (a != a || b != b) ? sde_f_nan() : (b < a ? b : a); }
 __device__ __forceinline__ double sde_f_max(double a, double b) { return (a != a || b != b) ? sde_f_nan() : (b > a ? b : a); }
+
+// ---- f32 overloads (dtype = f32 plans; arithmetic = fast only, so no *_rn intrinsics are needed)
+__device__ __forceinline__ float sde_f_sq(float x) { return x * x; }
+__device__ __forceinline__ float sde_f_nanf() { return __int_as_float(0x7fc00000); }
+__device__ __forceinline__ bool sde_f_is0(float x) { return fabsf(x) <= SDE_F_EPS8F; }
+__device__ __forceinline__ float sde_f_not(float x) { return sde_f_is0(x) ? 1.0f : 0.0f; }
+__device__ __forceinline__ float sde_f_eq(float a, float b) { return fabsf(a - b) <= SDE_F_EPS8F ? 1.0f : 0.0f; }
+__device__ __forceinline__ float sde_f_ne(float a, float b) { return fabsf(a - b) <= SDE_F_EPS8F ? 0.0f : 1.0f; }
+__device__ __forceinline__ float sde_f_and(float a, float b) { return sde_f_is0(a) ? a : b; }
+__device__ __forceinline__ float sde_f_or(float a, float b) { return sde_f_is0(a) ? b : a; }
+__device__ __forceinline__ float sde_f_sign(float x) { return (x != x) ? x : (signbit(x) ? -1.0f : 1.0f); }
+__device__ __forceinline__ float sde_f_min(float a, float b) { return (a != a || b != b) ? sde_f_nanf() : (b < a ? b : a); }
+__device__ __forceinline__ float sde_f_max(float a, float b) { return (a != a || b != b) ? sde_f_nanf() : (b > a ? b : a); }

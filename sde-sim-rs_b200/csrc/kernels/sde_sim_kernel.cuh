@@ -72,7 +72,7 @@
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
 //   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | moment scratch
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
-#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0 && !SDE_DIRECT) ? (SDE_NW * 32 * SDE_TILE_LD * 8) : 0)
+#define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0 && !SDE_DIRECT) ? (((SDE_NW * 32 * SDE_TILE_LD * (int)sizeof(sde_real) + 7) & ~7)) : 0)
 #define SDE_SMEM_STEP_BYTES (SDE_TS * SDE_STEP_LD * 8)
 #define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * SDE_NW * 4) : 0)
 #define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * 32 * 4) : 0)
@@ -85,7 +85,7 @@
 #define SDE_PF_LANE ((SDE_TS * SDE_KK * 32 + SDE_BLOCK - 1) / SDE_BLOCK)
 #define SDE_PF_STEP ((SDE_TS + SDE_BLOCK - 1) / SDE_BLOCK)
 
-__device__ __forceinline__ double sde_uniform_to_draw(double u, bool wiener, const double* s_icdf, int lane) {
+__device__ __forceinline__ sde_real sde_uniform_to_draw(double u, bool wiener, const double* s_icdf, int lane) {
     if (!wiener) return u;                               // Poisson factors consume the uniform itself
 #if SDE_ICDF == 1
     return sde_icdf_normal_fast(u, s_icdf, lane);
@@ -111,10 +111,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     extern __shared__ double4 sde_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
     double* s_icdf = reinterpret_cast<double*>(smem);
-    double* s_tile = reinterpret_cast<double*>(smem + SDE_SMEM_ICDF_BYTES);
+    sde_real* s_tile = reinterpret_cast<sde_real*>(smem + SDE_SMEM_ICDF_BYTES);
     unsigned char* s_stage = smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES;     // two buffers of SDE_SMEM_STAGE_BYTES
     double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_BYTES - SDE_SMEM_MOM_BYTES);
     (void)s_icdf; (void)s_tile; (void)s_mom;
+    sde_real* const out_r = reinterpret_cast<sde_real*>(prm.out);   // rows are sde_real (f32 plans: float)
+    (void)out_r;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -221,10 +223,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     };
 
     // ScenarioFiltration::new — row 0 from initial_values, cache loaded from row 0 (filtration.rs:42-51)
-    double row[SDE_P], cache[SDE_P];
+    sde_real row[SDE_P], cache[SDE_P];
     double ct = __ldg(prm.times);
 #pragma unroll
-    for (int p = 0; p < SDE_P; ++p) { row[p] = __ldg(prm.x0 + p); cache[p] = row[p]; }
+    for (int p = 0; p < SDE_P; ++p) { row[p] = (sde_real)__ldg(prm.x0 + p); cache[p] = row[p]; }
 
 #if SDE_USES_CHACHA
     SdeChaCha8Stream cha;
@@ -234,22 +236,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #if SDE_OUT == 0
     if (valid) {
 #pragma unroll
-        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)s_local * T * SDE_P + p] = row[p];
+        for (int p = 0; p < SDE_P; ++p) out_r[(size_t)s_local * T * SDE_P + p] = row[p];
     }
 #if SDE_DIRECT
-    double* const my_row = prm.out + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's row [T][P]
+    sde_real* const my_row = out_r + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's row [T][P]
     // step shift of this warp: the group that starts at step gamma writes elements from (gamma+1) P on, and
     // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
     const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
 #else
-    double* my_tile = s_tile + (size_t)(warp * 32 + lane) * SDE_TILE_LD;
+    sde_real* my_tile = s_tile + (size_t)(warp * 32 + lane) * SDE_TILE_LD;
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
     const long long s_warp0 = s_local - lane;
 #endif
 #elif SDE_OUT == 1
     if (valid) {
 #pragma unroll
-        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)p * prm.n_paths + s_local] = row[p];
+        for (int p = 0; p < SDE_P; ++p) out_r[(size_t)p * prm.n_paths + s_local] = row[p];
     }
 #endif
 
@@ -271,7 +273,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         //   draw(t, j, ..)    uniforms -> normal / Poisson draws of step t (j = position in the group; it must be a
         //                     compile-time constant after unrolling so the ChaCha buffer is indexed statically)
         //   advance(t, ..)    one step of the scheme + staging of the new row
-        auto draw = [&](const int t, const int j, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+        auto draw = [&](const int t, const int j, sde_real (&zu)[SDE_KK], sde_real& u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             u0 = 0.0;
             zu[0] = 0.0;
@@ -339,7 +341,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #endif
         };
-        auto advance = [&](const int t, const double (&zu)[SDE_KK], const double u0) __attribute__((always_inline)) {
+        auto advance = [&](const int t, const sde_real (&zu)[SDE_KK], const sde_real u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
 #if SDE_OUT == 0 && !SDE_DIRECT
@@ -349,19 +351,19 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             if (valid) {
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p)
-                    prm.out[((size_t)(t + 1) * SDE_P + p) * prm.n_paths + s_local] = row[p];
+                    out_r[((size_t)(t + 1) * SDE_P + p) * prm.n_paths + s_local] = row[p];
             }
 #endif
         };
 #if SDE_DIRECT
-        double* group_dst = my_row;                           // running store pointer of the step groups
+        sde_real* group_dst = my_row;                           // running store pointer of the step groups
 #endif
         auto group = [&](const int tc) __attribute__((always_inline)) {
-            double zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
+            sde_real zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
 #if SDE_DIRECT
-            double vals[SDE_UNR * SDE_P];                     // rows tc+1 .. tc+4, in output order
+            sde_real vals[SDE_UNR * SDE_P];                     // rows tc+1 .. tc+4, in output order
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) {
                 advance(tc + j, zu[j], u0[j]);
@@ -370,7 +372,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
             {
                 // predicated (not branched) stores: dead lanes only exist in the first and last CTA
-                double* dst = group_dst;                      // = my_row + (tc + 1) P: 32-byte aligned by the choice of gamma
+                sde_real* dst = group_dst;                      // = my_row + (tc + 1) P: 32-byte aligned by the choice of gamma
                 group_dst += 4 * SDE_P;
                 const int live = valid ? 1 : 0;
 #pragma unroll
@@ -393,7 +395,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
         // one step on its own (ragged ends); direct mode stores its row element-wise
         auto single = [&](const int t, const int j) __attribute__((always_inline)) {
-            double zu[SDE_KK], u0;
+            sde_real zu[SDE_KK], u0;
             draw(t, j, zu, u0);
             advance(t, zu, u0);
 #if SDE_DIRECT
@@ -461,26 +463,26 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
         __syncwarp();
         {
-            const double* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
+            const sde_real* wt = s_tile + (size_t)warp * 32 * SDE_TILE_LD;
             constexpr int NC = SDE_TT * SDE_P;                 // columns of a full tile
             const size_t row_stride = (size_t)T * SDE_P;
             constexpr bool kRegularNC = (NC <= 32 && 32 % NC == 0) || (NC % 32 == 0);
             if (kRegularNC && t_end - t0 == SDE_TT && valid_mask == 0xffffffffu) {
                 // full tile, all 32 paths live
-                double* dst0 = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P;
+                sde_real* dst0 = out_r + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P;
                 if constexpr (NC <= 32 && 32 % NC == 0) {
                     // a warp store covers 32/NC rows; running pointers, one 64-bit add per store
                     constexpr int RPI = 32 / NC;
                     const int r0 = lane / NC, i0 = lane % NC;
-                    double* p = dst0 + (size_t)r0 * row_stride + i0;
-                    const double* q = wt + r0 * SDE_TILE_LD + i0;
+                    sde_real* p = dst0 + (size_t)r0 * row_stride + i0;
+                    const sde_real* q = wt + r0 * SDE_TILE_LD + i0;
 #pragma unroll
                     for (int it = 0; it < 32 / RPI; ++it) {
                         *p = q[it * RPI * SDE_TILE_LD];
                         p += RPI * row_stride;
                     }
                 } else {
-                    double* p = dst0 + lane;
+                    sde_real* p = dst0 + lane;
 #pragma unroll 4
                     for (int r = 0; r < 32; ++r) {
 #pragma unroll
@@ -491,8 +493,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             } else {
                 // partial tile and/or dead lanes: one row at a time, running pointers
                 const int ncols = (t_end - t0) * SDE_P;
-                double* p = prm.out + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P + lane;
-                const double* q = wt + lane;
+                sde_real* p = out_r + ((size_t)s_warp0 * T + (t0 + 1)) * SDE_P + lane;
+                const sde_real* q = wt + lane;
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     if ((valid_mask >> r) & 1u) {
@@ -511,13 +513,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #if SDE_OUT == 2
     if (valid) {
 #pragma unroll
-        for (int p = 0; p < SDE_P; ++p) prm.out[(size_t)s_local * SDE_P + p] = row[p];
+        for (int p = 0; p < SDE_P; ++p) out_r[(size_t)s_local * SDE_P + p] = row[p];
     }
 #elif SDE_OUT == 3
     // warp-shuffle + block reduction of (count, mean, M2) per process; fixed order => deterministic
     for (int p = 0; p < SDE_P; ++p) {
         SdeMoments m;
-        m.n = valid ? 1.0 : 0.0; m.mean = valid ? row[p] : 0.0; m.m2 = 0.0;
+        m.n = valid ? 1.0 : 0.0; m.mean = valid ? (double)row[p] : 0.0; m.m2 = 0.0;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             SdeMoments o;

@@ -24,7 +24,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (ARITH_FAST, ARITH_STRICT, ICDF_FAST, ICDF_REFERENCE, ICDF_SINGLE, LAYOUT_NTP, LAYOUT_TPN, OUT_MOMENTS,
+from ._ffi import (ARITH_FAST, ARITH_STRICT, DTYPE_F32, DTYPE_F64, ICDF_FAST, ICDF_REFERENCE, ICDF_SINGLE, LAYOUT_NTP, LAYOUT_TPN, OUT_MOMENTS,
                    OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
                    SCRAMBLE_XOR)
 
@@ -34,6 +34,7 @@ __all__ = ["simulate", "parse_equations", "Universe", "Plan", "Filtration", "sha
 _OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
 _LAYOUTS = {"NTP": LAYOUT_NTP, "TPN": LAYOUT_TPN}
 _SCRAMBLES = {"cp_shift_per_path": SCRAMBLE_CP_SHIFT_PER_PATH, "xor": SCRAMBLE_XOR, "none": SCRAMBLE_NONE}
+_DTYPES = {"f64": DTYPE_F64, "float64": DTYPE_F64, "f32": DTYPE_F32, "float32": DTYPE_F32}
 _ICDFS = {"reference": ICDF_REFERENCE, "fast": ICDF_FAST, "single": ICDF_SINGLE}
 _ARITHS = {"strict": ARITH_STRICT, "fast": ARITH_FAST}
 _RKS = {"reference": RK_REFERENCE, "textbook": RK_TEXTBOOK}
@@ -86,7 +87,7 @@ def parse_equations(processes_equations: Sequence[str], time_steps: Sequence[flo
 
 def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, layout: str, scramble: str, icdf: str,
                   arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0,
-                  min_blocks: int = 0, ntp_direct: int = 0):
+                  min_blocks: int = 0, ntp_direct: int = 0, dtype: str = "f64"):
     o = _ffi.default_options()
     o.device = device
     o.seed = seed & (2**64 - 1)
@@ -102,6 +103,7 @@ def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, 
     o.block_threads = block_threads
     o.min_blocks = min_blocks
     o.ntp_direct = ntp_direct
+    o.dtype = _pick(_DTYPES, dtype, "dtype")
     return o
 
 
@@ -117,8 +119,10 @@ class Plan:
     def __init__(self, universe: Universe, scheme: str = "euler", rng_method: str = "pseudo", *, output: str = "paths",
                  layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
                  arithmetic: str = "strict", rk_variant: str = "reference", device: Optional[int] = None,
-                 inject=None, tile_steps: int = 0, block_threads: int = 0, min_blocks: int = 0, ntp_direct: int = 0):
+                 inject=None, tile_steps: int = 0, block_threads: int = 0, min_blocks: int = 0, ntp_direct: int = 0,
+                 dtype: str = "f64"):
         self.universe = universe
+        self.dtype = "f32" if _pick(_DTYPES, dtype, "dtype") == DTYPE_F32 else "f64"
         self.scheme, self.rng_method = scheme, rng_method
         self.output, self.layout = output, layout
         self.device = _current_device() if device is None else int(device)
@@ -126,7 +130,7 @@ class Plan:
         opts = _make_options(device=self.device, seed=0, scenario_offset=0, output=output, layout=layout,
                              scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant,
                              inject_ptr=(inject.data_ptr() if inject is not None else 0), tile_steps=tile_steps,
-                             block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct)
+                             block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct, dtype=dtype)
         h = C.c_void_p()
         rc = _ffi.lib().sde_plan_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), C.byref(h))
         _ffi.check(rc, prefix_runtime="Simulation failed: ")
@@ -164,10 +168,11 @@ class Plan:
         if scenarios <= 0:
             raise ValueError("scenarios must be a positive integer")
         shape = self.output_shape(scenarios)
+        tdt = torch.float32 if (self.dtype == "f32" and self.output != "moments") else torch.float64
         if out is None:
-            out = torch.empty(shape, dtype=torch.float64, device=f"cuda:{self.device}")
-        elif tuple(out.shape) != tuple(shape) or out.dtype != torch.float64 or not out.is_cuda or not out.is_contiguous():
-            raise ValueError(f"out must be a contiguous CUDA float64 tensor of shape {shape}")
+            out = torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+        elif tuple(out.shape) != tuple(shape) or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CUDA {tdt} tensor of shape {shape}")
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         names, vals, n = self._init_arrays(initial_values)
@@ -187,11 +192,13 @@ class Plan:
         if scenarios <= 0:
             raise ValueError("scenarios must be a positive integer")
         shape = self.output_shape(scenarios)
+        ndt = np.float32 if (self.dtype == "f32" and self.output != "moments") else np.float64
         if out is None:
-            out = np.empty(shape, dtype=np.float64)
+            out = np.empty(shape, dtype=ndt)
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
-        if int(np.prod(out.shape)) != int(np.prod(shape)):
-            raise ValueError(f"out must hold {shape} float64 values")
+        isz = out.element_size() if hasattr(out, "element_size") else out.itemsize
+        if int(np.prod(out.shape)) != int(np.prod(shape)) or isz != np.dtype(ndt).itemsize:
+            raise ValueError(f"out must hold {shape} {np.dtype(ndt).name} values")
         names, vals, n = self._init_arrays(initial_values)
         nl = C.c_int(0)
         rc = _ffi.lib().sde_plan_run_host(self._h, names, vals.ctypes.data_as(C.c_void_p), n, scenarios,
@@ -293,13 +300,15 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
              initial_values: Dict[str, float], rng_method: str = "pseudo", scheme: str = "euler", *,
              seed: Optional[int] = None, output: str = "paths", layout: str = "NTP",
              scramble: str = "cp_shift_per_path", icdf: str = "reference", arithmetic: str = "strict",
-             rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0) -> Filtration:
+             rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0,
+             dtype: str = "f64") -> Filtration:
     """Drop-in for sde_sim_rs.simulate (src/py_binding.rs:10-18; defaults as in python/sde_sim_rs/sde_sim_rs.pyi:11-12).
 
     Keyword-only extensions: `seed` (the reference draws a fresh OS-entropy seed per call,
     src/sim/mod.rs:28-29 — so does this when seed is None), `output` paths|terminal|moments, `layout`,
     `scramble` cp_shift_per_path (reference behaviour) | xor | none, `icdf` reference|fast|single,
-    `arithmetic` strict|fast, `rk_variant` reference|textbook, `device`, `scenario_offset`.
+    `arithmetic` strict|fast, `rk_variant` reference|textbook, `device`, `scenario_offset`, `dtype` f64|f32
+    (f32: state, arithmetic and stored values in single precision; needs arithmetic="fast").
     """
     if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
         raise ValueError("scenarios must be a positive integer")                      # py_binding.rs:20-24
@@ -307,7 +316,8 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
         seed = int.from_bytes(os.urandom(8), "little")
     # parse first so that equation errors surface as ValueError before any CUDA work (py_binding.rs:30-32)
     plan = _cached_plan(list(processes_equations), time_steps, scheme, rng_method, output=output, layout=layout,
-                        scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant, device=device)
+                        scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant, device=device,
+                        dtype=dtype)
     values = plan.run(dict(initial_values), int(scenarios), seed=seed, scenario_offset=scenario_offset)
     return Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output, layout=layout,
                       scenario_offset=scenario_offset, seed=seed)

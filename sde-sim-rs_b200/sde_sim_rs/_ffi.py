@@ -19,6 +19,7 @@ OUT_PATHS, OUT_TERMINAL, OUT_MOMENTS = 0, 1, 2
 LAYOUT_NTP, LAYOUT_TPN = 0, 1
 SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_XOR, SCRAMBLE_NONE = 0, 1, 2
 ICDF_REFERENCE, ICDF_FAST, ICDF_SINGLE = 0, 1, 2
+DTYPE_F64, DTYPE_F32 = 0, 1
 ARITH_STRICT, ARITH_FAST = 0, 1
 RK_REFERENCE, RK_TEXTBOOK = 0, 1
 
@@ -41,6 +42,7 @@ class SdeOptions(C.Structure):
         ("block_threads", C.c_int32),
         ("min_blocks", C.c_int32),
         ("ntp_direct", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 

@@ -85,7 +85,7 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"),
-                        ntp_direct=kw.get("ntp_direct", 0))
+                        ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"))
     src, nb = C.c_void_p(), C.c_size_t(0)
     rc = _ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), compile, C.byref(src), C.byref(nb))
     _ffi.check(rc)
@@ -97,6 +97,16 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
 def test_unknown_scheme_is_value_error():
     with pytest.raises(ValueError, match="unknown scheme"):
         _lower(GBM_EQ, grid(252, 4), "milstein", "pseudo", compile=0)
+
+
+def test_f32_needs_fast_arithmetic_and_emits_float_literals():
+    with pytest.raises(ValueError, match="f32 needs arithmetic"):
+        _lower(GBM_EQ, grid(252, 4), "euler", "pseudo", compile=0, dtype="f32")
+    text, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, dtype="f32", arithmetic="fast")
+    assert "#define SDE_F32 1" in text and "0.0500000007f" in text and "0.5f" in text
+    assert "0.05 " not in text.split("sde_model_step(")[1]             # no f64 literal inside the model step
+    text64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, arithmetic="fast")
+    assert "SDE_F32" not in text64 and "0.050000000000000003" in text64
 
 
 def test_rk_without_factor_is_value_error():
@@ -122,6 +132,8 @@ def test_lowering_cache_rule_euler_vs_rk():
     ("C2-compat", GBM_EQ, grid(252), "euler", "sobol", {}),
     ("C2-tiled", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast", "ntp_direct": 2}),
     ("C3-full-euler-resident", HESTON_EQ, grid(250), "euler", "sobol", {"scramble": "xor", "icdf": "fast"}),
+    ("C2-f32", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "icdf": "single", "arithmetic": "fast", "dtype": "f32"}),
+    ("C3-f32", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal", "arithmetic": "fast", "dtype": "f32"}),
     ("C2-tpn", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "layout": "TPN"}),
     ("C3", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor"}),
     ("C3-terminal", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal"}),

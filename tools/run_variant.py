@@ -24,11 +24,12 @@ D = 252
 times = [k / D for k in range(D + 1)]
 N = int(sys.argv[1])
 runs = int(os.environ.get("RUNS", 3))
-out = torch.empty((N, D + 1, 1), dtype=torch.float64, device="cuda")
+DTYPE = os.environ.get("DTYPE", "f64")
+out = torch.empty((N, D + 1, 1), dtype=torch.float32 if DTYPE == "f32" else torch.float64, device="cuda")
 for spec in sys.argv[2:]:
     f = [int(x) for x in spec.split(",")] + [0]
     plan = S.Plan(S.Universe(GBM, times), "euler", "sobol", scramble="xor", ntp_direct=f[0], block_threads=f[1], min_blocks=f[2],
-                  tile_steps=f[3], icdf=os.environ.get("ICDF", "fast"), arithmetic="fast")
+                  tile_steps=f[3], icdf=os.environ.get("ICDF", "fast"), arithmetic="fast", dtype=DTYPE)
     plan.run({"X1": 1.0}, N, seed=42, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -262,6 +262,12 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
         grid = std::min<uint64_t>((items + warps - 1) / warps, (uint64_t)sm_count(opt_.device) * (uint64_t)low_.min_blocks);
     }
     if (grid == 0 || n == 0) return;
+    if (low_.resident) {
+        // the <= 5 leading and <= 127 trailing pad lanes of a launch store their (meaningless) rows here: one scratch row
+        size_t need = ((size_t)u_.T() * u_.P() + 8) * 8;
+        if (d_partials_.bytes() < need) { cu_check(d.cuStreamSynchronize(stream), "cuStreamSynchronize"); d_partials_.alloc(need); }
+        prm.partials = d_partials_.ptr();
+    }
     if (grid > 0x7fffffffull) throw ExprError{"too many scenarios for one launch"};
     if (opt_.lower.out == OUT_MOMENTS) {
         size_t need = (size_t)grid * u_.P() * 3 * 8;

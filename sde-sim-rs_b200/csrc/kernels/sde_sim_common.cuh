@@ -22,7 +22,7 @@ struct SdeParams {
     const sde_u32* xor_masks;   // [S*K]         32-bit digital-shift masks
     const double* inject;     // [N][S][K+1]
     double* out;
-    double* partials;         // moments: [grid][P][3]
+    double* partials;         // moments: [grid][P][3]; persistent kernel: scratch row [T*P + 4] for the pad lanes' stores
 };
 
 struct SdeMoments { double n, mean, m2; };

@@ -160,7 +160,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         double ct = t_first;
 #pragma unroll
         for (int p = 0; p < SDE_P; ++p) { row[p] = x0[p]; cache[p] = x0[p]; }
-        double* const my_row = prm.out + (size_t)(valid ? s_local : 0) * T * SDE_P;      // this path's rows [T][P]
+        // this path's rows [T][P].  Pad lanes (they only exist in the first and last item of a launch) are pointed at a
+        // scratch row with the same phase modulo a sector, so the group stores of the step loop need no predicate
+        double* const my_row = valid ? prm.out + (size_t)s_local * T * SDE_P
+                                     : prm.partials + (size_t)(((long long)s_local * T * SDE_P) & 3);
         // step shift of this warp: the group that starts at step gamma writes elements from (gamma + 1) P on, and
         // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
         const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
@@ -274,6 +277,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         const int live = (valid && prm.reserved == 12345) ? 1 : 0;   // profiling aid: group stores predicated off
 #else
         const int live = valid ? 1 : 0;
+        (void)live;
 #endif
         // advance_group: the sequential state updates of one group (rows t+1 .. t+GRP collected in output order) and
         // their predicated (not branched) full-sector stores: dead lanes only exist in the first and last item
@@ -287,7 +291,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #pragma unroll
             for (int q = 0; q < SDE_P * (SDE_RES_GRP / 4); ++q) {
-#if SDE_ST256
+#if SDE_ST256 && !defined(SDE_DEBUG_NOSTORE)
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                             ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
+#elif SDE_ST256
                 asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
                              ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
 #else

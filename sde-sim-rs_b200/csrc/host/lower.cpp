@@ -28,6 +28,8 @@ class StepGen {
     // so that constants which do not change along the time grid can be emitted as literals instead of table reads
     std::vector<std::vector<double>> slot_values;
     std::vector<double> model_consts;                        // literal coefficients placed in __constant__ memory (sde_mc[])
+    bool matrix = false;                                     // the step was emitted in matrix form (wide linear model)
+    std::string matrix_decl() const { return matrix_decl_.str(); }
     std::string prelude() const { return pre_.str(); }      // declarations emitted before the step body
 
     // Emits the body of sde_model_step given the cache position on entry; returns it on exit.
@@ -54,6 +56,9 @@ class StepGen {
             hoist_ = n <= 16;
         }
         const int P = u_.P();
+        matrix_decl_.str("");
+        matrix = matrix_form_ok();
+        if (matrix) { emit_matrix_form(); return state_; }
         for (int p = 0; p < P; ++p) line("sde_real n" + std::to_string(p) + " = " + format_real(0.0) + ";");   // row t+1 is zero until set (filtration.rs:28)
         if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
         for (int p = 0; p < P; ++p) line("row[" + std::to_string(p) + "] = n" + std::to_string(p) + ";");
@@ -66,6 +71,7 @@ class StepGen {
     CacheAt state_ = OLD;
     std::ostringstream* o_ = nullptr;
     std::ostringstream pre_;
+    std::ostringstream matrix_decl_;
     std::vector<bool> w_declared_;
     bool hoist_ = true;
 
@@ -115,6 +121,70 @@ class StepGen {
         }
         // with a stale cache (steady state entered AT times[t]) c[p] is not X_p(t): keep the literal form
         return true;
+    }
+
+    // Matrix form of a wide linear model (arithmetic=fast, Euler): every process is Levy with coefficients a_j X_p on
+    // dt / dW_k only (a Cholesky-loaded GBM basket).  One step is X_i *= A_i + sum_k M[i][k] w_k with w_k = sqrt(dt) z_k.
+    // Written out term by term that is thousands of FMAs with distinct literal loadings: a 150 KB step that streams through
+    // the instruction cache and pins every draw in a register (255 registers, 2 warps per scheduler).  Here it is emitted
+    // as loops over blocks of 8 processes with the loadings in constant memory ([block][k][8]: uniform 128-bit loads),
+    // the draws and the rows in (L1-resident) local arrays: a few KB of code at ~80 registers.  Same FMA order per
+    // process as the term-by-term form (k ascending onto A_i), so the results are bit-identical to it.
+    bool matrix_form_ok() const {
+        if (opt_.strict || opt_.scheme != SCHEME_EULER || hoist_) return false;
+        if (!u_.algebraic_indices.empty() || u_.P() < 16 || u_.K() < 16) return false;
+        double lin[128];
+        for (int p = 0; p < u_.P(); ++p) {
+            const Process& pr = u_.processes[p];
+            if (!pr.levy || !linear_in_own_state(pr, p, lin)) return false;
+            for (const Term& t : pr.terms) if (t.kind == IncKind::Poisson) return false;
+        }
+        return true;
+    }
+    void emit_matrix_form() {
+        const int P = u_.P(), K = u_.K(), NB = (P + 7) / 8;
+        std::vector<double> drift(NB * 8, 0.0), M((size_t)NB * K * 8, 0.0);
+        std::vector<int> kend(NB, 0);
+        double lin[128];
+        for (int p = 0; p < P; ++p) {
+            const Process& pr = u_.processes[p];
+            linear_in_own_state(pr, p, lin);
+            for (size_t j = 0; j < pr.terms.size(); ++j) {
+                const Term& t = pr.terms[j];
+                if (t.kind == IncKind::Time) drift[p] += lin[j];
+                else { M[((size_t)(p / 8) * K + t.factor) * 8 + (p % 8)] += lin[j]; kend[p / 8] = std::max(kend[p / 8], t.factor + 1); }
+            }
+        }
+        matrix_decl_ << "__constant__ sde_real sde_ma[" << NB * 8 << "] = {";
+        for (size_t i = 0; i < drift.size(); ++i) matrix_decl_ << (i ? ", " : "") << format_real(drift[i]);
+        matrix_decl_ << "};\n__constant__ sde_real sde_mm[" << M.size() << "] = {";
+        for (size_t i = 0; i < M.size(); ++i) matrix_decl_ << (i ? ", " : "") << format_real(M[i]);
+        matrix_decl_ << "};\n";
+        line("// matrix form (see lower.cpp): X_i *= A_i + sum_k M[i][k] sqrt(dt) z_k, blocks of 8 processes");
+        line("sde_real w[SDE_KK];");
+        line("#pragma unroll 4");
+        line("for (int k = 0; k < SDE_K; ++k) w[k] = sqrt_dt * zu[k];");
+        // the block loop is written out (NB copies of a small rolled k-loop with literal bounds): every constant-memory
+        // address is then a loop counter plus a literal, which ptxas keeps on the uniform datapath (LDCU.128: two
+        // loadings per instruction) — indexed through a runtime block number it falls back to per-thread LDC.64
+        for (int b = 0; b < NB; ++b) {
+            const std::string sb = std::to_string(b * 8), off = std::to_string((size_t)b * K * 8);
+            line("{   // processes " + sb + " .. " + std::to_string(std::min(P, b * 8 + 8) - 1));
+            line("    sde_real g[8];");
+            line("#pragma unroll");
+            line("    for (int j = 0; j < 8; ++j) g[j] = fma(sde_ma[" + sb + " + j], dt, " + format_real(1.0) + ");");
+            line("#pragma unroll 4");
+            line("    for (int k = 0; k < " + std::to_string(kend[b]) + "; ++k) {");
+            line("        const sde_real wk = w[k];");
+            line("#pragma unroll");
+            line("        for (int j = 0; j < 8; ++j) g[j] = fma(sde_mm[" + off + " + k * 8 + j], wk, g[j]);");
+            line("    }");
+            for (int j = 0; j < 8 && b * 8 + j < P; ++j)
+                line("    row[" + std::to_string(b * 8 + j) + "] = row[" + std::to_string(b * 8 + j) + "] * g[" + std::to_string(j) + "];");
+            line("}");
+        }
+        line("ct = t_cur;");
+        state_ = CUR;                                        // as after the refresh of the term-by-term form
     }
 
     void euler() {                                           // src/sim/euler.rs:5-37
@@ -381,7 +451,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         // measured on B200 (tools/sweep.py, profiles/r1_sweep_c2.json): with 4-step groups the kernel wants ~100 registers
         // (the next tile's prefetched words stay in registers behind the last group); 2 CTAs x 256 threads at a
         // 128-register cap beat 3-4 CTAs at 85 / 64 registers (409 vs 403 / 376 G path-steps/s on C2)
-        const int regs_est = std::min(255, (L.unr >= 4 ? 96 : 52) + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
+        // (matrix-form steps keep the draws and the rows in local arrays: ~85 registers whatever P and K are;
+        //  measured on the 64-asset basket: 3 CTAs x 256 threads 1.46-1.51 vs 1 CTA 1.03 G path-steps/s)
+        const int regs_est = gen.matrix ? 85 : std::min(255, (L.unr >= 4 ? 96 : 52) + 6 * P + 2 * K + (opt.scheme == SCHEME_RK ? 4 * P : 0));
         int by_regs = std::max(1, 65536 / (L.block * regs_est));
         int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / std::max<size_t>(L.smem_bytes, 1024));
         int by_threads = std::max(1, 2048 / L.block);
@@ -430,7 +502,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
-    {
+    if (K > 0 && std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; })) {
+        s << "true";                                         // (also keeps the predicate free when k is a runtime loop index)
+    } else {
         bool any = false;
         for (int k = 0; k < K; ++k) if (u.factor_is_wiener[k]) { s << (any ? " || " : "") << "k == " << k; any = true; }
         if (!any) s << "false";
@@ -443,6 +517,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "    (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)slots;\n";
     for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << table_slots[i] << ";\n";
     s << "}\n";
+    if (gen.matrix) s << gen.matrix_decl();
     if (!gen.model_consts.empty()) {
         s << "__constant__ sde_real sde_mc[" << gen.model_consts.size() << "] = {";
         for (size_t i = 0; i < gen.model_consts.size(); ++i) s << (i ? ", " : "") << format_real(gen.model_consts[i]);

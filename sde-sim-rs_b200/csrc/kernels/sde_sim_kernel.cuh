@@ -286,7 +286,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 u0 = __ldg(src + SDE_K);
             }
 #else
+            // wide models: a partially unrolled loop keeps 4 inverse-normal chains in flight and lets the draws live in a
+            // (L1-resident) local array instead of 2 K registers; ChaCha modes index their block buffer statically
+#if SDE_K >= 16 && !SDE_USES_CHACHA
+#pragma unroll 4
+#else
 #pragma unroll
+#endif
             for (int k = 0; k < SDE_K; ++k) {
 #if SDE_USES_CHACHA
                 const int slot = (j * SDE_K + k) & 7;      // compile-time after unrolling

@@ -14,7 +14,7 @@ from conftest import basket_equations, grid  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 eqs, init = basket_equations(64)
 for kw in (dict(icdf="fast", arithmetic="fast"),):
-    shapes = ((0, 0), (128, 1), (128, 2), (256, 1), (64, 1)) if not os.environ.get("C4_ONE") else ((0, 0),)
+    shapes = ((0, 0), (256, 2), (256, 3), (128, 4), (128, 6), (512, 1), (512, 2)) if not os.environ.get("C4_ONE") else ((0, 0),)
     for block, mb in shapes:
         try:
             plan = S.Plan(S.Universe(eqs, grid(252)), "euler", "sobol", output="moments", scramble="xor", block_threads=block, min_blocks=mb, **kw)

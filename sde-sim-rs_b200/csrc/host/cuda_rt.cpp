@@ -19,6 +19,7 @@ extern "C" {
 extern const char sde_blob_sim_kernel_cuh_begin[], sde_blob_sim_kernel_cuh_end[];
 extern const char sde_blob_sim_common_cuh_begin[], sde_blob_sim_common_cuh_end[];
 extern const char sde_blob_sim_resident_cuh_begin[], sde_blob_sim_resident_cuh_end[];
+extern const char sde_blob_sim_wide_cuh_begin[], sde_blob_sim_wide_cuh_end[];
 extern const char sde_blob_device_rng_cuh_begin[], sde_blob_device_rng_cuh_end[];
 extern const char sde_blob_device_icdf_cuh_begin[], sde_blob_device_icdf_cuh_end[];
 extern const char sde_blob_icdf_tables_cuh_begin[], sde_blob_icdf_tables_cuh_end[];
@@ -213,6 +214,7 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
         {"sde_sim_kernel.cuh", sde_blob_sim_kernel_cuh_begin, sde_blob_sim_kernel_cuh_end},
         {"sde_sim_common.cuh", sde_blob_sim_common_cuh_begin, sde_blob_sim_common_cuh_end},
         {"sde_sim_resident.cuh", sde_blob_sim_resident_cuh_begin, sde_blob_sim_resident_cuh_end},
+        {"sde_sim_wide.cuh", sde_blob_sim_wide_cuh_begin, sde_blob_sim_wide_cuh_end},
         {"sde_device_rng.cuh", sde_blob_device_rng_cuh_begin, sde_blob_device_rng_cuh_end},
         {"sde_device_icdf.cuh", sde_blob_device_icdf_cuh_begin, sde_blob_device_icdf_cuh_end},
         {"sde_icdf_tables.cuh", sde_blob_icdf_tables_cuh_begin, sde_blob_icdf_tables_cuh_end},

@@ -159,7 +159,21 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
     if (uses_sobol(opt_.lower.rng) && dims > 0) {
         std::vector<uint32_t> V, lane, nib;
         sobol_tables((uint32_t)dims, V, lane, &nib, low_.direct ? 4u : 1u);
-        if (low_.resident) {
+        if (low_.wide) {
+            // sde_sim_wide.cuh reads the lane part in A-fragment order: [S][NKK][MT][32], entry (t, kk, m, l) =
+            // x_d(8m + (l >> 2)) for d = t K + 4kk + (l & 3) (zero for the pad factors of the last factor step)
+            const size_t K = (size_t)u_.K(), NKK = (size_t)low_.wide_nkk, MT = (size_t)low_.wide_mt;
+            std::vector<uint32_t> lt((size_t)S * NKK * MT * 32, 0u);
+            for (size_t t = 0; t < (size_t)S; ++t)
+                for (size_t kk = 0; kk < NKK; ++kk)
+                    for (size_t m = 0; m < MT; ++m)
+                        for (size_t l = 0; l < 32; ++l) {
+                            const size_t k = 4 * kk + (l & 3);
+                            if (k < K) lt[((t * NKK + kk) * MT + m) * 32 + l] = lane[(t * K + k) * 32 + 8 * m + (l >> 2)];
+                        }
+            lane.swap(lt);
+        }
+        if (low_.resident || low_.wide) {
             // sde_sim_resident.cuh reads the nibble table dimension-fastest: [8][16][ld], ld = dims rounded up to 32
             const size_t ld = (dims + 31) & ~(size_t)31;
             std::vector<uint32_t> nt(128 * ld, 0u);
@@ -254,6 +268,13 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
     prm.inject = (CUdeviceptr)d_inject;
     prm.out = (CUdeviceptr)d_out;
     uint64_t grid = (first_n + n - prm.n_base + block - 1) / block;
+    if (low_.wide) {
+        // persistent warps: one work item = 8 wide_mt paths, see sde_sim_wide.cuh
+        const uint64_t wp = 8ull * (uint64_t)low_.wide_mt;
+        const uint64_t items = (first_n + n - (first_n & ~(wp - 1)) + wp - 1) / wp;
+        const uint64_t warps = block / 32;
+        grid = std::min<uint64_t>((items + warps - 1) / warps, (uint64_t)sm_count(opt_.device));
+    }
     if (low_.resident) {
         // persistent warps: one work item = 32 paths (lane stride 4 inside a 128-path block), see sde_sim_resident.cuh
         const uint64_t base128 = first_n & ~127ull;
@@ -269,8 +290,9 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
         prm.partials = d_partials_.ptr();
     }
     if (grid > 0x7fffffffull) throw ExprError{"too many scenarios for one launch"};
+    const uint64_t n_partials = low_.wide ? grid * (block / 32) : grid;      // the wide kernel leaves one partial per warp
     if (opt_.lower.out == OUT_MOMENTS) {
-        size_t need = (size_t)grid * u_.P() * 3 * 8;
+        size_t need = (size_t)n_partials * u_.P() * 3 * 8;
         if (d_partials_.bytes() < need) { cu_check(d.cuStreamSynchronize(stream), "cuStreamSynchronize"); d_partials_.alloc(need); }
         prm.partials = d_partials_.ptr();
     }
@@ -280,7 +302,7 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
     if (n_launches) ++*n_launches;
     if (opt_.lower.out == OUT_MOMENTS) {
         CUdeviceptr parts = d_partials_.ptr();
-        uint64_t np = grid;
+        uint64_t np = n_partials;
         CUdeviceptr outp = (CUdeviceptr)d_out;
         void* fargs[] = {&parts, &np, &outp};
         cu_check(d.cuLaunchKernel(fn_fin_, 1, 1, 1, 256, 1, 1, 0, stream, fargs, nullptr), "cuLaunchKernel(sde_moments_finalize)");

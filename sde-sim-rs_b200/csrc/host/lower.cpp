@@ -29,6 +29,8 @@ class StepGen {
     std::vector<std::vector<double>> slot_values;
     std::vector<double> model_consts;                        // literal coefficients placed in __constant__ memory (sde_mc[])
     bool matrix = false;                                     // the step was emitted in matrix form (wide linear model)
+    std::vector<double> mat_drift, mat_M;                    // matrix form: a_i [NB*8] and loadings M [NB][K][8]
+    std::vector<int> mat_kend;                               // matrix form: factors used by each block of 8 processes
     std::string matrix_decl() const { return matrix_decl_.str(); }
     std::string prelude() const { return pre_.str(); }      // declarations emitted before the step body
 
@@ -155,6 +157,7 @@ class StepGen {
                 else { M[((size_t)(p / 8) * K + t.factor) * 8 + (p % 8)] += lin[j]; kend[p / 8] = std::max(kend[p / 8], t.factor + 1); }
             }
         }
+        mat_drift = drift; mat_M = M; mat_kend = kend;
         matrix_decl_ << "__constant__ sde_real sde_ma[" << NB * 8 << "] = {";
         for (size_t i = 0; i < drift.size(); ++i) matrix_decl_ << (i ? ", " : "") << format_real(drift[i]);
         matrix_decl_ << "};\n__constant__ sde_real sde_mm[" << M.size() << "] = {";
@@ -415,7 +418,37 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         if (opt.direct == 2 && !L.resident)
             throw ExprError{"the persistent-warp kernel needs Sobol (xor / none) full-path NTP output, K <= 2 and (T-1)*K*128 B of shared memory"};
     }
-    if (!L.resident) {
+    // Wide linear model reduced to terminal values / moments under the XOR digital shift: the correlation product runs
+    // on the FP64 tensor path (sde_sim_wide.cuh).  A lane keeps 8 wide_mt paths x (2 NB state + NKK draw) doubles in
+    // registers: two row tiles per warp when that is <= 64 doubles, else one.
+    if (gen.matrix && opt.wide_mma != 0 && opt.rng == RNG_SOBOL_XOR && (opt.out == OUT_TERMINAL || opt.out == OUT_MOMENTS) && !opt.f32) {
+        const int NB = (P + 7) / 8, NKK = (K + 3) / 4, S = u.T() - 1;
+        const int per_tile = 2 * NB + NKK;
+        const int mt = 2 * per_tile <= 64 ? 2 : (per_tile <= 64 ? 1 : 0);
+        // measured on B200 (64 assets, tools/run_c4.py): 16 warps per SM at a 128-register cap (a few hundred bytes of
+        // L1-resident spills) beat 8 warps at 255 registers, 3.72 vs 3.47 G path-steps/s — the dependent DMMA chains
+        // and the 19-deep inverse-normal chains want the extra warps more than the registers
+        int block = opt.block > 0 ? std::max(32, std::min(1024, (opt.block / 32) * 32)) : 512;
+        auto wide_smem = [&](int blk, bool wide_tab) {       // mirrors the SDE_SMEM_* macros of sde_sim_wide.cuh
+            size_t icdf = (opt.icdf == 1) ? (wide_tab ? (size_t)1024 * 2 * 8 * 8 : (size_t)(128 * 2 * 8 + 64) * 8) : 0;
+            size_t mom = opt.out == OUT_MOMENTS ? (size_t)(blk / 32) * NB * 8 * 3 * 8 : 0;
+            return icdf + (size_t)NB * NKK * 32 * 8 + (size_t)NB * 8 * 8 + mom + (size_t)(blk / 32) * NKK * 4 * 4;
+        };
+        if (mt > 0 && (size_t)S * K < (1u << 31) && wide_smem(block, false) <= 220 * 1024) {
+            L.wide = true;
+            L.wide_mt = mt; L.wide_nb = NB; L.wide_nkk = NKK;
+            L.icdf_wide = opt.icdf == 1 && wide_smem(block, true) <= 220 * 1024 && !std::getenv("SDE_B200_NO_WIDE_TABLE");
+            L.block = block;
+            L.min_blocks = 1;
+            L.smem_bytes = wide_smem(block, L.icdf_wide);
+            L.tt = S;
+        }
+    }
+    if (opt.wide_mma == 1 && !L.wide)
+        throw ExprError{"the tensor-core kernel for wide models needs a linear Levy model with P, K >= 16 (arithmetic=\"fast\", euler), "
+                        "sobol with scramble=\"xor\" and terminal / moments output"};
+    if (L.wide) {
+    } else if (!L.resident) {
     int tt = opt.tile_steps;
     if (tt <= 0) {
         tt = 32;
@@ -483,9 +516,23 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "#define SDE_P " << P << "\n#define SDE_K " << K << "\n#define SDE_KK " << KK << "\n";
     s << "#define SDE_SCHEME " << opt.scheme << "\n#define SDE_RNG " << opt.rng << "\n#define SDE_OUT " << opt.out << "\n";
     if (opt.f32) s << "#define SDE_F32 1\n";
+    if (const char* d = std::getenv("SDE_B200_DEFINES")) {       // tuning only: "NAME=VALUE;NAME=VALUE" -> #define lines
+        std::string item;
+        std::istringstream ds(d);
+        while (std::getline(ds, item, ';')) {
+            if (item.empty()) continue;
+            const size_t eq = item.find('=');
+            s << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+        }
+    }
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
+    if (L.wide) {
+        s << "#define SDE_S " << (u.T() - 1) << "\n#define SDE_WNB " << L.wide_nb << "\n#define SDE_WNKK " << L.wide_nkk
+          << "\n#define SDE_WMT " << L.wide_mt << "\n";
+        if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
+    }
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";
         if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
@@ -517,7 +564,25 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     s << "    (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)slots;\n";
     for (int i = 0; i < nslot; ++i) s << "    slots[" << i << "] = " << table_slots[i] << ";\n";
     s << "}\n";
-    if (gen.matrix) s << gen.matrix_decl();
+    if (gen.matrix && !L.wide) s << gen.matrix_decl();
+    if (L.wide) {
+        // loadings in mma.m8n8k4 B-fragment order: entry (j, kk, lane) = M[process 8j + (lane >> 2)][factor 4kk + (lane & 3)]
+        const int NB = L.wide_nb, NKK = L.wide_nkk;
+        s << "__device__ const double sde_wm[" << NB * NKK * 32 << "] = {";
+        for (int j = 0; j < NB; ++j)
+            for (int kk = 0; kk < NKK; ++kk)
+                for (int l = 0; l < 32; ++l) {
+                    const int k = 4 * kk + (l & 3);
+                    const double v = k < K ? gen.mat_M[((size_t)j * K + k) * 8 + (l >> 2)] : 0.0;
+                    s << ((j || kk || l) ? ", " : "") << format_real(v);
+                }
+        s << "};\n__device__ const double sde_wa[" << NB * 8 << "] = {";
+        for (int i = 0; i < NB * 8; ++i) s << (i ? ", " : "") << format_real(gen.mat_drift[i]);
+        s << "};\n// factor steps (of 4) process tile j needs: its loadings are zero beyond\n";
+        s << "__device__ __forceinline__ constexpr int sde_wkk_end(int j) {\n    constexpr int e[" << NB << "] = {";
+        for (int j = 0; j < NB; ++j) s << (j ? ", " : "") << (gen.mat_kend[j] + 3) / 4;
+        s << "};\n    return e[j];\n}\n";
+    }
     if (!gen.model_consts.empty()) {
         s << "__constant__ sde_real sde_mc[" << gen.model_consts.size() << "] = {";
         for (size_t i = 0; i < gen.model_consts.size(); ++i) s << (i ? ", " : "") << format_real(gen.model_consts[i]);
@@ -528,8 +593,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
          "                                               const sde_real u0, const double* __restrict__ ss) {\n";
     s << "    const sde_real t_cur = (sde_real)ss[0], t_next = (sde_real)ss[1], dt = (sde_real)ss[2], sqrt_dt = (sde_real)ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
-    s << gen.prelude() << body.str();
-    s << "}\n#include \"" << (L.resident ? "sde_sim_resident.cuh" : "sde_sim_kernel.cuh") << "\"\n";
+    if (L.wide) s << "    // (the step lives in sde_sim_wide.cuh: X_i *= 1 + a_i dt + sqrt(dt) sum_k M[i][k] z_k on the FP64 tensor path)\n";
+    else s << gen.prelude() << body.str();
+    s << "}\n#include \"" << (L.wide ? "sde_sim_wide.cuh" : (L.resident ? "sde_sim_resident.cuh" : "sde_sim_kernel.cuh")) << "\"\n";
     L.source = s.str();
     return L;
 }

@@ -28,6 +28,8 @@ struct LowerOptions {
     int min_blocks = 0;      // 0 = auto: CTAs per SM promised to the compiler (__launch_bounds__)
     int direct = -1;         // NTP paths: -1 = auto, 0 = shared-memory transpose, 1 = direct sector stores (tiled kernel),
                              // 2 = persistent-warp kernel with resident tables (sde_sim_resident.cuh)
+    int wide_mma = -1;       // wide linear models, terminal / moments: -1 = auto, 0 = time-tiled kernel, 1 = require the
+                             // FP64 tensor-core kernel (sde_sim_wide.cuh)
 };
 
 struct Lowered {
@@ -41,6 +43,9 @@ struct Lowered {
     bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory
+    bool wide = false;       // tensor-core kernel for wide linear models (sde_sim_wide.cuh): persistent warps, 8 wide_mt paths per warp
+    int wide_mt = 0;         // row tiles (of 8 paths) per warp
+    int wide_nb = 0, wide_nkk = 0;   // process tiles of 8 / factor steps of 4
     bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)
 };
 

@@ -50,6 +50,9 @@
 #define SDE_FULL_SECTORS (SDE_P == 1 && SDE_S >= 8 && SDE_ST256)   /* row heads / tails leave as whole sectors */
 #endif
 #endif
+#ifndef SDE_ST_HINT
+#define SDE_ST_HINT ""                         /* cache operator of the group stores (tuning: ".cs", ".wt", ".cg") */
+#endif
 #define SDE_NW (SDE_BLOCK / 32)
 #define SDE_SK (SDE_S * SDE_K)
 #define SDE_STEP_LD (4 + SDE_NSLOT)
@@ -292,7 +295,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
             for (int q = 0; q < SDE_P * (SDE_RES_GRP / 4); ++q) {
 #if SDE_ST256 && !defined(SDE_DEBUG_NOSTORE)
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                asm volatile("st.global" SDE_ST_HINT ".v4.f64 [%0], {%1, %2, %3, %4};"
                              ::"l"(dst + 4 * q), "d"(vals[4 * q]), "d"(vals[4 * q + 1]), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]) : "memory");
 #elif SDE_ST256
                 asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"

@@ -87,7 +87,7 @@ def parse_equations(processes_equations: Sequence[str], time_steps: Sequence[flo
 
 def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, layout: str, scramble: str, icdf: str,
                   arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0,
-                  min_blocks: int = 0, ntp_direct: int = 0, dtype: str = "f64"):
+                  min_blocks: int = 0, ntp_direct: int = 0, dtype: str = "f64", wide_mma: int = 0):
     o = _ffi.default_options()
     o.device = device
     o.seed = seed & (2**64 - 1)
@@ -104,6 +104,7 @@ def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, 
     o.min_blocks = min_blocks
     o.ntp_direct = ntp_direct
     o.dtype = _pick(_DTYPES, dtype, "dtype")
+    o.wide_mma = wide_mma
     return o
 
 
@@ -120,7 +121,7 @@ class Plan:
                  layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
                  arithmetic: str = "strict", rk_variant: str = "reference", device: Optional[int] = None,
                  inject=None, tile_steps: int = 0, block_threads: int = 0, min_blocks: int = 0, ntp_direct: int = 0,
-                 dtype: str = "f64"):
+                 dtype: str = "f64", wide_mma: int = 0):
         self.universe = universe
         self.dtype = "f32" if _pick(_DTYPES, dtype, "dtype") == DTYPE_F32 else "f64"
         self.scheme, self.rng_method = scheme, rng_method
@@ -130,7 +131,8 @@ class Plan:
         opts = _make_options(device=self.device, seed=0, scenario_offset=0, output=output, layout=layout,
                              scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant,
                              inject_ptr=(inject.data_ptr() if inject is not None else 0), tile_steps=tile_steps,
-                             block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct, dtype=dtype)
+                             block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct, dtype=dtype,
+                             wide_mma=wide_mma)
         h = C.c_void_p()
         rc = _ffi.lib().sde_plan_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), C.byref(h))
         _ffi.check(rc, prefix_runtime="Simulation failed: ")

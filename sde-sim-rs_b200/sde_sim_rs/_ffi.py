@@ -43,6 +43,7 @@ class SdeOptions(C.Structure):
         ("min_blocks", C.c_int32),
         ("ntp_direct", C.c_int32),
         ("dtype", C.c_int32),
+        ("wide_mma", C.c_int32),
     ]
 
 

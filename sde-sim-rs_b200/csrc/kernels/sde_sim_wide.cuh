@@ -49,7 +49,11 @@
 #define SDE_SMEM_WA_BYTES (SDE_WPP * 8)
 #define SDE_SMEM_BW_BYTES (SDE_NW * SDE_WKP * 4)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * SDE_WPP * 3 * 8) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_WM_BYTES + SDE_SMEM_WA_BYTES + SDE_SMEM_MOM_BYTES + SDE_SMEM_BW_BYTES)
+#ifndef SDE_WIDE_XS
+#define SDE_WIDE_XS 0                          /* 1: the state X lives in shared memory (C-fragment order) instead of registers */
+#endif
+#define SDE_SMEM_XS_BYTES (SDE_WIDE_XS ? (SDE_NW * SDE_WMT * SDE_WNB * 32 * 16) : 0)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_WM_BYTES + SDE_SMEM_WA_BYTES + SDE_SMEM_MOM_BYTES + SDE_SMEM_XS_BYTES + SDE_SMEM_BW_BYTES)
 
 __device__ __forceinline__ void sde_dmma884(double (&c)[2], const double a, const double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -63,7 +67,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
     double* s_wa = s_wm + SDE_WNB * SDE_WNKK * 32;
     double* s_mom = s_wa + SDE_WPP;
     sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_BYTES - SDE_SMEM_BW_BYTES);
-    (void)s_icdf; (void)s_mom;
+    double2* s_xs = reinterpret_cast<double2*>(smem + SDE_SMEM_BYTES - SDE_SMEM_BW_BYTES - SDE_SMEM_XS_BYTES);
+    (void)s_icdf; (void)s_mom; (void)s_xs;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -88,6 +93,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
     __syncthreads();
 
     sde_u32* const my_bw = s_bw + warp * SDE_WKP;
+#if SDE_WIDE_XS
+    double2* const my_xs = s_xs + warp * (SDE_WMT * SDE_WNB * 32) + lane;     // entry (m, j): my_xs[(m NB + j) 32]
+#endif
 #if SDE_OUT == 3
     double* const my_mom = s_mom + warp * SDE_WPP * 3;
 #endif
@@ -119,6 +127,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
             for (int q = 0; q < 8; ++q) off[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
         }
         // ScenarioFiltration::new — row 0 from initial_values (filtration.rs:42-50), in C-fragment layout
+#if SDE_WIDE_XS
+#pragma unroll
+        for (int j = 0; j < SDE_WNB; ++j) {
+            const int p = 8 * j + 2 * fc;
+            const double2 v = make_double2(p < SDE_P ? __ldg(prm.x0 + p) : 0.0, p + 1 < SDE_P ? __ldg(prm.x0 + p + 1) : 0.0);
+#pragma unroll
+            for (int m = 0; m < SDE_WMT; ++m) my_xs[(m * SDE_WNB + j) * 32] = v;
+        }
+#else
         double X[SDE_WMT][SDE_WNB][2];
 #pragma unroll
         for (int j = 0; j < SDE_WNB; ++j)
@@ -129,6 +146,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
 #pragma unroll
                 for (int m = 0; m < SDE_WMT; ++m) X[m][j][e] = v;
             }
+#endif
 
 #pragma unroll 1
         for (int t = 0; t < S; ++t) {
@@ -189,11 +207,28 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
                 const double g0 = fma(a.x, dt, 1.0), g1 = fma(a.y, dt, 1.0);
 #pragma unroll
                 for (int m = 0; m < SDE_WMT; ++m) {
+#if SDE_WIDE_XS
+                    double2 xv = my_xs[(m * SDE_WNB + j) * 32];
+                    xv.x *= fma(acc[m][0], sq, g0);
+                    xv.y *= fma(acc[m][1], sq, g1);
+                    my_xs[(m * SDE_WNB + j) * 32] = xv;
+#else
                     X[m][j][0] *= fma(acc[m][0], sq, g0);
                     X[m][j][1] *= fma(acc[m][1], sq, g1);
+#endif
                 }
             }
         }
+#if SDE_WIDE_XS
+        double X[SDE_WMT][SDE_WNB][2];                        // terminal values back into registers for the epilogue
+#pragma unroll
+        for (int m = 0; m < SDE_WMT; ++m)
+#pragma unroll
+            for (int j = 0; j < SDE_WNB; ++j) {
+                const double2 xv = my_xs[(m * SDE_WNB + j) * 32];
+                X[m][j][0] = xv.x; X[m][j][1] = xv.y;
+            }
+#endif
 
 #if SDE_OUT == 2
 #pragma unroll

@@ -234,7 +234,8 @@ std::string Expr::emit_node(int i, bool strict, const std::string& c, const std:
         case Op::Mod: return "fmod(" + A(0) + ", " + A(1) + ")";
         case Op::Pow: {
             const ExprNode& ex = nodes_[n.args[1]];
-            if (ex.op == Op::Const && ex.value == 0.5) return "sqrt(" + A(0) + ")";   // powf(x, 0.5): equal except for -0.0 / -inf
+            // powf(x, 0.5): equal to sqrt except for -0.0 / -inf; arithmetic=fast takes the MUFU seed + one cubic step (<= 1 ulp)
+            if (ex.op == Op::Const && ex.value == 0.5) return std::string(strict ? "sqrt(" : "sde_f_sqrt_fast(") + A(0) + ")";
             if (ex.op == Op::Const && ex.value == 2.0) return "sde_f_sq(" + A(0) + ")";
             if (ex.op == Op::Const && ex.value == 1.0) return A(0);
             return "pow(" + A(0) + ", " + A(1) + ")";

@@ -85,7 +85,7 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"),
-                        ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"))
+                        ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"), wide_mma=kw.get("wide_mma", 0))
     src, nb = C.c_void_p(), C.c_size_t(0)
     rc = _ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), compile, C.byref(src), C.byref(nb))
     _ffi.check(rc)
@@ -147,6 +147,31 @@ def test_configs_lower_and_compile_for_sm100a(name, eqs, times, scheme, rng, kw)
     assert ('#include "sde_sim_kernel.cuh"' in text or '#include "sde_sim_resident.cuh"' in text) and nbytes > 10_000
     if name == "C2-xor-fast":                                           # Sobol full paths with resident tables: persistent warps
         assert '#include "sde_sim_resident.cuh"' in text and "#define SDE_S 252" in text
+
+
+def test_wide_linear_models_lower_to_the_tensor_core_kernel():
+    from conftest import basket_equations
+
+    fast = {"scramble": "xor", "icdf": "fast", "arithmetic": "fast"}
+    eqs, _ = basket_equations(64)
+    text, nbytes = _lower(eqs, grid(252), "euler", "sobol", compile=1, output="moments", **fast)       # C4: auto selection
+    assert '#include "sde_sim_wide.cuh"' in text and nbytes > 10_000
+    assert "#define SDE_WNB 8" in text and "#define SDE_WNKK 16" in text and "#define SDE_WMT 2" in text
+    # triangular Cholesky loadings: process tile j needs 2 (j + 1) factor steps of 4
+    assert "constexpr int e[8] = {2, 4, 6, 8, 10, 12, 14, 16};" in text
+    # B fragments: entry (j = 0, kk = 0, lane 0) = M[0][0] = sigma_0 * L[0][0] = 0.1
+    assert "sde_wm[4096] = {0.10000000000000001," in text
+    off, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="moments", wide_mma=1, **fast)
+    assert '#include "sde_sim_kernel.cuh"' in off                                                     # switched off: time-tiled kernel
+    paths, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="paths", **fast)
+    assert '#include "sde_sim_kernel.cuh"' in paths                                                   # full paths are not its business
+    strict, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="moments", scramble="xor")
+    assert '#include "sde_sim_kernel.cuh"' in strict                                                  # reference arithmetic keeps the term order
+    eq20, _ = basket_equations(20)                                                                    # pad tiles: P = K = 20 -> 3 x 8, 5 x 4
+    t20, nb20 = _lower(eq20, grid(252, 12), "euler", "sobol", compile=1, output="terminal", wide_mma=2, **fast)
+    assert "#define SDE_WNB 3" in t20 and "#define SDE_WNKK 5" in t20 and nb20 > 10_000
+    with pytest.raises(ValueError, match="tensor-core kernel"):
+        _lower(GBM_EQ, grid(252, 4), "euler", "sobol", compile=0, output="moments", wide_mma=2, **fast)
 
 
 def test_joe_kuo_table_matches_scipy(oracle):

@@ -421,7 +421,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     // Wide linear model reduced to terminal values / moments under the XOR digital shift: the correlation product runs
     // on the FP64 tensor path (sde_sim_wide.cuh).  A lane keeps 8 wide_mt paths x (2 NB state + NKK draw) doubles in
     // registers: two row tiles per warp when that is <= 64 doubles, else one.
-    if (gen.matrix && opt.wide_mma != 0 && opt.rng == RNG_SOBOL_XOR && (opt.out == OUT_TERMINAL || opt.out == OUT_MOMENTS) && !opt.f32) {
+    if (gen.matrix && opt.wide_mma != 0 && opt.rng == RNG_SOBOL_XOR && opt.out != OUT_PATHS_TPN && !opt.f32) {
         const int NB = (P + 7) / 8, NKK = (K + 3) / 4, S = u.T() - 1;
         const int per_tile = 2 * NB + NKK;
         const int mt = 2 * per_tile <= 64 ? 2 : (per_tile <= 64 ? 1 : 0);
@@ -449,7 +449,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     }
     if (opt.wide_mma == 1 && !L.wide)
         throw ExprError{"the tensor-core kernel for wide models needs a linear Levy model with P, K >= 16 (arithmetic=\"fast\", euler), "
-                        "sobol with scramble=\"xor\" and terminal / moments output"};
+                        "sobol with scramble=\"xor\", f64, and [N][T][P] paths / terminal / moments output"};
     if (L.wide) {
     } else if (!L.resident) {
     int tt = opt.tile_steps;

@@ -3,7 +3,8 @@
 // Same contract as sde_sim_kernel.cuh (one launch = the parallel region of sim::simulate, src/sim/mod.rs:41-88),
 // selected by the lowering when the model is a Cholesky-loaded basket — every process Levy with coefficients
 // a_j X_i on dt / dW_k only (src/sim/euler.rs:15-28 applied to `( a * S_i ) * dW_k` terms) — driven by scrambled
-// Sobol points and reduced to terminal values or moments (BASELINE config C4: 64 assets, 64 factors).  One Euler
+// Sobol points (BASELINE config C4: 64 assets, 64 factors, terminal moments; full paths in reference order and terminal
+// values as well).  One Euler
 // step of such a model is
 //     X_i <- X_i * (1 + a_i dt + sqrt(dt) * sum_k M[i][k] z_k),
 // i.e. per step a [paths x K] * [K x P] matrix product in f64: GEMM-shaped work, so it runs on the FP64 tensor
@@ -31,8 +32,8 @@
 #pragma once
 #include "sde_sim_common.cuh"
 
-#if SDE_RNG != 2 || !(SDE_OUT == 2 || SDE_OUT == 3)
-#error "sde_sim_wide.cuh: Sobol with XOR digital shift, terminal values or moments only"
+#if SDE_RNG != 2 || !(SDE_OUT == 0 || SDE_OUT == 2 || SDE_OUT == 3)
+#error "sde_sim_wide.cuh: Sobol with XOR digital shift; full paths [N][T][P], terminal values or moments"
 #endif
 #ifndef SDE_ICDF_WIDE
 #define SDE_ICDF_WIDE 0
@@ -148,6 +149,24 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
             }
 #endif
 
+#if SDE_OUT == 0
+        // full paths in reference order [N][T][P] (filtration.rs:87-113): the 4 lanes of a fragment row write 8 consecutive
+        // processes of one path's row, 64 contiguous bytes = two whole sectors per (m, j)
+        double* row_ptr[SDE_WMT];
+#pragma unroll
+        for (int m = 0; m < SDE_WMT; ++m) {
+            row_ptr[m] = prm.out + (size_t)(valid[m] ? s_local[m] : 0) * (S + 1) * SDE_P + 2 * fc;
+            if (valid[m]) {
+#pragma unroll
+                for (int j = 0; j < SDE_WNB; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int p = 8 * j + 2 * fc + e;
+                        if (p < SDE_P) row_ptr[m][8 * j + e] = __ldg(prm.x0 + p);
+                    }
+            }
+        }
+#endif
 #pragma unroll 1
         for (int t = 0; t < S; ++t) {
             // ---- warp part of this step's dimensions, digital shift folded in: my_bw[k] = x_d(n0) ^ mask_d, d = t K + k
@@ -215,6 +234,20 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
 #else
                     X[m][j][0] *= fma(acc[m][0], sq, g0);
                     X[m][j][1] *= fma(acc[m][1], sq, g1);
+                    const double2 xv = make_double2(X[m][j][0], X[m][j][1]);
+#endif
+#if SDE_OUT == 0
+                    if (valid[m]) {
+                        double* dst = row_ptr[m] + (size_t)(t + 1) * SDE_P + 8 * j;
+                        if ((SDE_P & 1) == 0 && 8 * j + 8 <= SDE_P) {
+                            *reinterpret_cast<double2*>(dst) = xv;             // P even: 16-byte aligned
+                        } else {
+                            if (8 * j + 2 * fc < SDE_P) dst[0] = xv.x;
+                            if (8 * j + 2 * fc + 1 < SDE_P) dst[1] = xv.y;
+                        }
+                    }
+#else
+                    (void)xv;
 #endif
                 }
             }
@@ -230,7 +263,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
             }
 #endif
 
-#if SDE_OUT == 2
+#if SDE_OUT == 0
+        // rows already stored step by step
+#elif SDE_OUT == 2
 #pragma unroll
         for (int m = 0; m < SDE_WMT; ++m)
             if (valid[m]) {

@@ -84,10 +84,27 @@ def test_auto_selection_and_refusal():
     eqs, init = basket_equations(64)
     times = grid(252, 8)
     assert "sde_sim_wide.cuh" in _plan(eqs, times, "moments", 0).source          # auto: qualifies
-    assert "sde_sim_wide.cuh" not in _plan(eqs, times, "paths", 0).source        # full paths stay on the time-tiled kernel
+    assert "sde_sim_wide.cuh" in _plan(eqs, times, "paths", 0).source
+    tpn = S.Plan(S.Universe(eqs, times), "euler", "sobol", output="paths", layout="TPN", scramble="xor", icdf="fast", arithmetic="fast")
+    assert "sde_sim_wide.cuh" not in tpn.source                                    # the transposed layout stays on the time-tiled kernel
     with pytest.raises(ValueError):                                                # required but not a wide linear model
         S.Plan(S.Universe(["dX1 = ( 0.05 * X1 ) * dt + ( 0.1 * X1) * dW1"], times), "euler", "sobol", output="moments",
                scramble="xor", icdf="fast", arithmetic="fast", wide_mma=2)
+
+
+@pytest.mark.parametrize("n_assets,N,off", [(64, 40, 0), (20, 37, 6), (33, 21, 0)])
+def test_full_paths_in_reference_order(oracle, n_assets, N, off):
+    # [N][T][P] rows incl. the t0 row (filtration.rs:87-113): 128-bit row stores (P even, whole tiles) and the scalar tail / odd-P path
+    eqs, init = basket_equations(n_assets)
+    times = grid(252, 40)
+    plan = _plan(eqs, times, "paths", 2)
+    got = plan.run(init, N, seed=13, scenario_offset=off).cpu().numpy()
+    ref = oracle.simulate(oracle.Universe(eqs, times), init, N, "euler", "sobol", seed=13, scramble="xor", scenario_offset=off)
+    assert got.shape == ref.shape == (N, 41, n_assets)
+    assert rel_err(got, ref) <= 1e-12, rel_err(got, ref)
+    # same rows through the host-buffer call (chunked launches + D2H)
+    host = plan.run_host(init, N, seed=13, scenario_offset=off)
+    assert np.array_equal(np.asarray(host).reshape(got.shape), got)
 
 
 def test_shard_union_equals_single_run():

@@ -163,8 +163,10 @@ def test_wide_linear_models_lower_to_the_tensor_core_kernel():
     assert "sde_wm[4096] = {0.10000000000000001," in text
     off, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="moments", wide_mma=1, **fast)
     assert '#include "sde_sim_kernel.cuh"' in off                                                     # switched off: time-tiled kernel
-    paths, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="paths", **fast)
-    assert '#include "sde_sim_kernel.cuh"' in paths                                                   # full paths are not its business
+    paths, _ = _lower(eqs, grid(252), "euler", "sobol", compile=1, output="paths", **fast)
+    assert '#include "sde_sim_wide.cuh"' in paths and "#define SDE_OUT 0" in paths                     # [N][T][P] rows too
+    tpn, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="paths", layout="TPN", **fast)
+    assert '#include "sde_sim_kernel.cuh"' in tpn                                                     # the transposed layout is not its business
     strict, _ = _lower(eqs, grid(252), "euler", "sobol", compile=0, output="moments", scramble="xor")
     assert '#include "sde_sim_kernel.cuh"' in strict                                                  # reference arithmetic keeps the term order
     eq20, _ = basket_equations(20)                                                                    # pad tiles: P = K = 20 -> 3 x 8, 5 x 4

@@ -429,17 +429,14 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         // L1-resident spills) beat 8 warps at 255 registers, 3.72 vs 3.47 G path-steps/s — the dependent DMMA chains
         // and the 19-deep inverse-normal chains want the extra warps more than the registers
         int block = opt.block > 0 ? std::max(32, std::min(1024, (opt.block / 32) * 32)) : 512;
-        const bool xs = std::getenv("SDE_B200_WIDE_XS") != nullptr;   // tuning: state in shared memory instead of registers
         auto wide_smem = [&](int blk, bool wide_tab) {       // mirrors the SDE_SMEM_* macros of sde_sim_wide.cuh
             size_t icdf = (opt.icdf == 1) ? (wide_tab ? (size_t)1024 * 2 * 8 * 8 : (size_t)(128 * 2 * 8 + 64) * 8) : 0;
             size_t mom = opt.out == OUT_MOMENTS ? (size_t)(blk / 32) * NB * 8 * 3 * 8 : 0;
-            size_t xsb = xs ? (size_t)(blk / 32) * mt * NB * 32 * 16 : 0;
-            return icdf + (size_t)NB * NKK * 32 * 8 + (size_t)NB * 8 * 8 + mom + xsb + (size_t)(blk / 32) * NKK * 4 * 4;
+            return icdf + (size_t)NB * NKK * 32 * 8 + (size_t)NB * 8 * 8 + mom + (size_t)(blk / 32) * NKK * 4 * 4;
         };
         if (mt > 0 && (size_t)S * K < (1u << 31) && wide_smem(block, false) <= 220 * 1024) {
             L.wide = true;
             L.wide_mt = mt; L.wide_nb = NB; L.wide_nkk = NKK;
-            L.wide_xs = xs;
             L.icdf_wide = opt.icdf == 1 && wide_smem(block, true) <= 220 * 1024 && !std::getenv("SDE_B200_NO_WIDE_TABLE");
             L.block = block;
             L.min_blocks = 1;
@@ -450,8 +447,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     if (opt.wide_mma == 1 && !L.wide)
         throw ExprError{"the tensor-core kernel for wide models needs a linear Levy model with P, K >= 16 (arithmetic=\"fast\", euler), "
                         "sobol with scramble=\"xor\", f64, and [N][T][P] paths / terminal / moments output"};
-    if (L.wide) {
-    } else if (!L.resident) {
+    if (!L.wide && !L.resident) {
     int tt = opt.tile_steps;
     if (tt <= 0) {
         tt = 32;
@@ -497,7 +493,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         if (opt.min_blocks > 0) L.min_blocks = std::min(opt.min_blocks, std::min(by_smem, by_threads));
     }
 
-    } else {
+    } else if (L.resident) {
         const int by_smem = (int)std::max<size_t>(1, (size_t)(224 * 1024) / (L.smem_bytes + 1024));
         const int by_threads = std::max(1, 2048 / L.block);
         // one CTA per SM: its warps are the persistent workers (see the block-size note above); opt.min_blocks can ask
@@ -535,7 +531,6 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         s << "#define SDE_S " << (u.T() - 1) << "\n#define SDE_WNB " << L.wide_nb << "\n#define SDE_WNKK " << L.wide_nkk
           << "\n#define SDE_WMT " << L.wide_mt << "\n";
         if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
-        if (L.wide_xs) s << "#define SDE_WIDE_XS 1\n";
     }
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";

@@ -44,7 +44,6 @@ struct Lowered {
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory
     bool wide = false;       // tensor-core kernel for wide linear models (sde_sim_wide.cuh): persistent warps, 8 wide_mt paths per warp
-    bool wide_xs = false;    // wide kernel: state in shared memory
     int wide_mt = 0;         // row tiles (of 8 paths) per warp
     int wide_nb = 0, wide_nkk = 0;   // process tiles of 8 / factor steps of 4
     bool enter_eq = false;   // steady-state: cache.time == times[t] on entry to a step (stale-cache case)

@@ -50,11 +50,7 @@
 #define SDE_SMEM_WA_BYTES (SDE_WPP * 8)
 #define SDE_SMEM_BW_BYTES (SDE_NW * SDE_WKP * 4)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * SDE_WPP * 3 * 8) : 0)
-#ifndef SDE_WIDE_XS
-#define SDE_WIDE_XS 0                          /* 1: the state X lives in shared memory (C-fragment order) instead of registers */
-#endif
-#define SDE_SMEM_XS_BYTES (SDE_WIDE_XS ? (SDE_NW * SDE_WMT * SDE_WNB * 32 * 16) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_WM_BYTES + SDE_SMEM_WA_BYTES + SDE_SMEM_MOM_BYTES + SDE_SMEM_XS_BYTES + SDE_SMEM_BW_BYTES)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_WM_BYTES + SDE_SMEM_WA_BYTES + SDE_SMEM_MOM_BYTES + SDE_SMEM_BW_BYTES)
 
 __device__ __forceinline__ void sde_dmma884(double (&c)[2], const double a, const double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -68,8 +64,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
     double* s_wa = s_wm + SDE_WNB * SDE_WNKK * 32;
     double* s_mom = s_wa + SDE_WPP;
     sde_u32* s_bw = reinterpret_cast<sde_u32*>(smem + SDE_SMEM_BYTES - SDE_SMEM_BW_BYTES);
-    double2* s_xs = reinterpret_cast<double2*>(smem + SDE_SMEM_BYTES - SDE_SMEM_BW_BYTES - SDE_SMEM_XS_BYTES);
-    (void)s_icdf; (void)s_mom; (void)s_xs;
+    (void)s_icdf; (void)s_mom;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -94,9 +89,6 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
     __syncthreads();
 
     sde_u32* const my_bw = s_bw + warp * SDE_WKP;
-#if SDE_WIDE_XS
-    double2* const my_xs = s_xs + warp * (SDE_WMT * SDE_WNB * 32) + lane;     // entry (m, j): my_xs[(m NB + j) 32]
-#endif
 #if SDE_OUT == 3
     double* const my_mom = s_mom + warp * SDE_WPP * 3;
 #endif
@@ -128,15 +120,6 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
             for (int q = 0; q < 8; ++q) off[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
         }
         // ScenarioFiltration::new — row 0 from initial_values (filtration.rs:42-50), in C-fragment layout
-#if SDE_WIDE_XS
-#pragma unroll
-        for (int j = 0; j < SDE_WNB; ++j) {
-            const int p = 8 * j + 2 * fc;
-            const double2 v = make_double2(p < SDE_P ? __ldg(prm.x0 + p) : 0.0, p + 1 < SDE_P ? __ldg(prm.x0 + p + 1) : 0.0);
-#pragma unroll
-            for (int m = 0; m < SDE_WMT; ++m) my_xs[(m * SDE_WNB + j) * 32] = v;
-        }
-#else
         double X[SDE_WMT][SDE_WNB][2];
 #pragma unroll
         for (int j = 0; j < SDE_WNB; ++j)
@@ -147,7 +130,6 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
 #pragma unroll
                 for (int m = 0; m < SDE_WMT; ++m) X[m][j][e] = v;
             }
-#endif
 
 #if SDE_OUT == 0
         // full paths in reference order [N][T][P] (filtration.rs:87-113): the 4 lanes of a fragment row write 8 consecutive
@@ -226,42 +208,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 1) sde_sim_kernel(const 
                 const double g0 = fma(a.x, dt, 1.0), g1 = fma(a.y, dt, 1.0);
 #pragma unroll
                 for (int m = 0; m < SDE_WMT; ++m) {
-#if SDE_WIDE_XS
-                    double2 xv = my_xs[(m * SDE_WNB + j) * 32];
-                    xv.x *= fma(acc[m][0], sq, g0);
-                    xv.y *= fma(acc[m][1], sq, g1);
-                    my_xs[(m * SDE_WNB + j) * 32] = xv;
-#else
                     X[m][j][0] *= fma(acc[m][0], sq, g0);
                     X[m][j][1] *= fma(acc[m][1], sq, g1);
-                    const double2 xv = make_double2(X[m][j][0], X[m][j][1]);
-#endif
 #if SDE_OUT == 0
                     if (valid[m]) {
                         double* dst = row_ptr[m] + (size_t)(t + 1) * SDE_P + 8 * j;
                         if ((SDE_P & 1) == 0 && 8 * j + 8 <= SDE_P) {
-                            *reinterpret_cast<double2*>(dst) = xv;             // P even: 16-byte aligned
+                            *reinterpret_cast<double2*>(dst) = make_double2(X[m][j][0], X[m][j][1]);   // P even: 16-byte aligned
                         } else {
-                            if (8 * j + 2 * fc < SDE_P) dst[0] = xv.x;
-                            if (8 * j + 2 * fc + 1 < SDE_P) dst[1] = xv.y;
+                            if (8 * j + 2 * fc < SDE_P) dst[0] = X[m][j][0];
+                            if (8 * j + 2 * fc + 1 < SDE_P) dst[1] = X[m][j][1];
                         }
                     }
-#else
-                    (void)xv;
 #endif
                 }
             }
         }
-#if SDE_WIDE_XS
-        double X[SDE_WMT][SDE_WNB][2];                        // terminal values back into registers for the epilogue
-#pragma unroll
-        for (int m = 0; m < SDE_WMT; ++m)
-#pragma unroll
-            for (int j = 0; j < SDE_WNB; ++j) {
-                const double2 xv = my_xs[(m * SDE_WNB + j) * 32];
-                X[m][j][0] = xv.x; X[m][j][1] = xv.y;
-            }
-#endif
 
 #if SDE_OUT == 0
         // rows already stored step by step

@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
-"""Throughput of every BASELINE.json config on one B200 (kernel time, CUDA events, device-resident output)
-beside the CPU oracle on a bounded sample.  Results -> gpurun_out/configs.json (copied to profiles/ by hand)."""
+"""Throughput of every BASELINE.json config on one B200 (kernel time, CUDA events, device-resident output).
+The CPU restatement's rate on a bounded sample of each config comes from tests/perf_cpu_oracle.py (the oracle is test
+infrastructure: only tests/, smoke() and bench.py's CPU legs execute it) and is merged in when its JSON is present.
+Results -> gpurun_out/configs.json (copied to profiles/ by hand)."""
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -13,9 +14,13 @@ for p in (ROOT, os.path.join(ROOT, "sde-sim-rs_b200"), os.path.join(ROOT, "tests
     sys.path.insert(0, p)
 import sde_sim_rs as S  # noqa: E402
 from conftest import GBM_EQ, HESTON_EQ, basket_equations, grid  # noqa: E402
-from oracle import oracle as orc  # noqa: E402
 
-CPU_THREADS = len(os.sched_getaffinity(0))
+CPU_RATES = {}
+try:
+    for r in json.load(open(os.path.join(ROOT, "gpurun_out", "cpu_oracle_rates.json"))):
+        CPU_RATES[r["config"]] = r
+except Exception:  # noqa: BLE001
+    pass
 
 
 def gpu_time(plan, init, N, reps=3, **kw):
@@ -34,13 +39,6 @@ def gpu_time(plan, init, N, reps=3, **kw):
     return e0.elapsed_time(e1) / reps
 
 
-def cpu_rate(eqs, times, init, N, scheme, rng, **kw):
-    U = orc.Universe(eqs, times)
-    t0 = time.perf_counter()
-    orc.simulate(U, init, N, scheme, rng, seed=42, nthreads=CPU_THREADS, **kw)
-    return N * (len(times) - 1) / (time.perf_counter() - t0)
-
-
 rows = []
 
 
@@ -55,10 +53,9 @@ def run(name, eqs, times, init, N, scheme, rng, n_cpu, plan_kw, cpu_kw=None, byt
             r["out_GBps"] = round(N * S_ * bytes_per_path_step / ms / 1e6, 1)
         rows.append(r)
         print(json.dumps(r), flush=True)
-    c = cpu_rate(eqs, times, init, n_cpu, scheme, rng, **(cpu_kw or {}))
-    r = {"config": name, "mode": "cpu-oracle", "N": n_cpu, "steps": S_, "threads": CPU_THREADS, "path_steps_per_s": c}
-    rows.append(r)
-    print(json.dumps(r), flush=True)
+    if name in CPU_RATES:
+        rows.append(CPU_RATES[name])
+        print(json.dumps(CPU_RATES[name]), flush=True)
 
 
 run("C1 GBM euler pseudo 10k x 252 full paths", GBM_EQ, grid(252), {"X1": 1.0}, 10_000, "euler", "pseudo", 10_000,

@@ -108,7 +108,8 @@ typedef struct sde_options {
     int32_t dtype;            /* enum sde_dtype: element type of the state, the model arithmetic and the stored rows.
                                * SDE_DTYPE_F32 needs arith = SDE_ARITH_FAST; paths / terminal buffers are then float,
                                * moments stay [P][3] f64 (accumulated in f64 from the f32 terminal values)                        */
-    int32_t wide_mma;         /* wide linear models (Cholesky-loaded baskets), terminal / moments output, SDE_SCRAMBLE_XOR:
+    int32_t wide_mma;         /* wide linear models (Cholesky-loaded baskets; SDE_SCRAMBLE_XOR, SDE_ARITH_FAST, f64; [N][T][P] paths,
+                               * terminal values or moments):
                                * 0 = auto (FP64 tensor-core kernel sde_sim_wide.cuh when the model qualifies); 1 = off (time-tiled
                                * kernel); 2 = required (plan creation fails when the model does not qualify)                      */
 } sde_options;

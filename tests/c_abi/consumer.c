@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
     sde_options_default(&opt);
     if (opt.struct_size != sizeof(sde_options)) { printf("struct size mismatch\n"); return 1; }
     opt.seed = seed;
-    if (strcmp(rng, "sobol") == 0) opt.scramble = 1;          /* SDE_SCRAMBLE_XOR */
+    if (strcmp(rng, "sobol") == 0) opt.scramble = SDE_SCRAMBLE_XOR;
 
     const char* names[1] = {"X1"};
     const double vals[1] = {1.0};

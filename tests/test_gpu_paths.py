@@ -314,6 +314,19 @@ def test_full_size_c2_properties():
     torch.cuda.empty_cache()
 
 
+def test_full_size_c5_per_gpu_moments_against_closed_form():
+    # C5's per-GPU share (2^30 paths x 365 steps, pseudo-random ChaCha8 streams, moments only): closed-form Euler-GBM moments
+    N, D = 1 << 30, 365
+    m = S.simulate(GBM_EQ, grid(D), N, {"X1": 1.0}, "pseudo", "euler", seed=2024, output="moments", icdf="fast",
+                   arithmetic="fast").to_numpy()[0]
+    assert m[0] == N
+    mu, sig, dt = 0.05, 0.1, 1.0 / D
+    mean = (1 + mu * dt) ** D
+    var = ((1 + mu * dt) ** 2 + sig * sig * dt) ** D - mean**2
+    assert abs(m[1] - mean) < 5 * np.sqrt(var / N)                            # 5 standard errors = 1.6e-5
+    assert abs(m[2] / (N - 1) / var - 1) < 1e-3                               # A&S perturbs Var(z) at ~1e-4
+
+
 # ---------------------------------------------------------------- ragged shapes (tile / group / sector edges)
 THREE_EQ = ["dA = ( 0.3 * (1.0 - A) ) * dt + ( 0.2 ) * dW1",
             "dB = ( 0.1 * B ) * dt + ( 0.3 * B ) * dW2",

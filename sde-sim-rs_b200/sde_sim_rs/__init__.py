@@ -28,7 +28,7 @@ from ._ffi import (ARITH_FAST, ARITH_STRICT, DTYPE_F32, DTYPE_F64, ICDF_FAST, IC
                    OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
                    SCRAMBLE_XOR)
 
-__all__ = ["simulate", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
+__all__ = ["simulate", "simulate_frame", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
            "cuda_available", "version"]
 
 _OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
@@ -328,6 +328,20 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
     values = plan.run(dict(initial_values), int(scenarios), seed=seed, scenario_offset=scenario_offset)
     return Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output, layout=layout,
                       scenario_offset=scenario_offset, seed=seed)
+
+
+def simulate_frame(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
+                   initial_values: Dict[str, float], rng_method: str = "pseudo", scheme: str = "euler", **kw):
+    """The reference's call with the reference's return value: the long DataFrame `scenario:i32, time:f64,
+    process_name:str, value:f64` in (scenario, time, process) row order (src/py_binding.rs:10-55,
+    src/filtration.rs:108-113) — a polars frame where polars is importable (what pyo3-polars hands back), a pandas
+    frame otherwise.  `simulate` itself returns the dense GPU tensor wrapped in a `Filtration`; this is the
+    convenience for scripts written against the reference package."""
+    res = simulate(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme, **kw)
+    try:
+        return res.to_polars()
+    except ImportError:
+        return res.to_pandas()
 
 
 # ---------------------------------------------------------------- multi-GPU helpers

@@ -388,3 +388,27 @@ def test_run_host_chunk_boundaries():
     assert torch.equal(host, dev.cpu())
     term_plan = S.Plan(S.Universe(GBM_EQ, times), "euler", "pseudo", output="terminal")
     assert np.array_equal(term_plan.run_host(init, 70_001, seed=4), term_plan.run(init, 70_001, seed=4).cpu().numpy())
+
+
+def test_simulate_frame_returns_the_reference_long_frame():
+    # the reference's call and return value (src/py_binding.rs:10-55): long frame, (scenario, time, process) row order
+    times, N = grid(252, 5), 7
+    df = S.simulate_frame(HESTON_EQ, times, N, {"S": 100.0, "v": 0.04}, "sobol", "euler", seed=3)
+    assert list(df.columns) == ["scenario", "time", "process_name", "value"] and len(df) == N * 6 * 2
+    dense = S.simulate(HESTON_EQ, times, N, {"S": 100.0, "v": 0.04}, "sobol", "euler", seed=3).to_numpy()
+    assert np.array_equal(np.asarray(df["value"], dtype=np.float64), dense.reshape(-1))
+    assert [str(x) for x in list(df["process_name"][:3])] == ["S", "v", "S"] and int(np.asarray(df["scenario"])[-1]) == N - 1
+
+
+@pytest.mark.parametrize("script", ["example_gbm.py", "example_jumps.py"])
+def test_examples_run(script):
+    import os
+    import subprocess
+    import sys
+
+    from conftest import PKG, ROOT
+
+    env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "scenario" in r.stdout and "process_name" in r.stdout

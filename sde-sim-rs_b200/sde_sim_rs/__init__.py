@@ -28,7 +28,7 @@ from ._ffi import (ARITH_FAST, ARITH_STRICT, DTYPE_F32, DTYPE_F64, ICDF_FAST, IC
                    OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
                    SCRAMBLE_XOR)
 
-__all__ = ["simulate", "simulate_frame", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
+__all__ = ["simulate", "simulate_frame", "simulate_devices", "simulate_sharded", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
            "cuda_available", "version"]
 
 _OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
@@ -362,6 +362,42 @@ def merge_moments(shards: np.ndarray) -> np.ndarray:
     out = np.zeros((P, 3), dtype=np.float64)
     _ffi.check(_ffi.lib().sde_moments_merge(shards.ctypes.data_as(C.c_void_p), n, P, out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+def simulate_devices(processes_equations, time_steps, scenarios, initial_values, rng_method="pseudo", scheme="euler", *,
+                     devices: Optional[Sequence[int]] = None, seed: Optional[int] = None, output: str = "paths", **kw):
+    """ONE process driving several GPUs of the box (the convenience for scripts; under torchrun use `simulate_sharded`):
+    device i of `devices` (default: all visible) simulates `shard_range(scenarios, i, len(devices))` with that scenario
+    offset — disjoint Sobol index ranges / ChaCha keys, no data-path exchange.  All launches are issued before any device
+    is synchronised.  Returns the list of per-device `Filtration` shards (paths / terminal values stay on their GPU, in
+    scenario order) or, for output="moments", one `Filtration` with the Chan-merged moments."""
+    import torch
+
+    if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
+        raise ValueError("scenarios must be a positive integer")
+    devs = list(range(torch.cuda.device_count())) if devices is None else [int(d) for d in devices]
+    if not devs:
+        raise RuntimeError("Simulation failed: no CUDA device (there is no CPU fallback)")
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    plans = [_cached_plan(list(processes_equations), time_steps, scheme, rng_method, output=output, device=d, **kw) for d in devs]
+    shards = []
+    for i, (d, plan) in enumerate(zip(devs, plans)):
+        lo, hi = shard_range(int(scenarios), i, len(devs))
+        if hi == lo:
+            continue
+        with torch.cuda.device(d):
+            values = plan.run(dict(initial_values), hi - lo, seed=seed, scenario_offset=lo)       # asynchronous on d's stream
+        shards.append(Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output,
+                                 layout=kw.get("layout", "NTP"), scenario_offset=lo, seed=seed))
+    for d in set(devs):
+        torch.cuda.synchronize(d)
+    if output != "moments":
+        return shards
+    merged = merge_moments(np.stack([s.to_numpy() for s in shards]))
+    first = shards[0]
+    return Filtration(torch.from_numpy(merged).to(first.values.device), first.time_steps, first.process_names, output=output,
+                      layout="NTP", scenario_offset=0, seed=seed)
 
 
 def simulate_sharded(processes_equations, time_steps, scenarios, initial_values, rng_method="pseudo", scheme="euler", *,

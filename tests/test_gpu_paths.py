@@ -412,3 +412,20 @@ def test_examples_run(script):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "scenario" in r.stdout and "process_name" in r.stdout
+
+
+def test_simulate_devices_union_equals_single_run():
+    # one process driving several GPUs: shards by scenario offset, union bit-identical to one run; moments Chan-merged.
+    # On a one-GPU box the same device is listed three times (three shards, same stream) — the sharding logic is what is tested.
+    devs = list(range(torch.cuda.device_count()))
+    devs = devs if len(devs) > 1 else [0, 0, 0]
+    times, N = grid(252, 30), 1001
+    kw = dict(seed=17, scramble="xor", icdf="fast", arithmetic="fast")
+    whole = S.simulate(GBM_EQ, times, N, {"X1": 1.0}, "sobol", "euler", **kw).to_numpy()
+    shards = S.simulate_devices(GBM_EQ, times, N, {"X1": 1.0}, "sobol", "euler", devices=devs, **kw)
+    assert [s.scenario_offset for s in shards] == [S.shard_range(N, i, len(devs))[0] for i in range(len(devs))]
+    assert np.array_equal(np.concatenate([s.to_numpy() for s in shards]), whole)
+    m = S.simulate_devices(GBM_EQ, times, N, {"X1": 1.0}, "sobol", "euler", devices=devs, output="moments", **kw).to_numpy()[0]
+    assert m[0] == N and abs(m[1] / whole[:, -1, 0].mean() - 1) <= 1e-13
+    tiny = S.simulate_devices(GBM_EQ, times, 2, {"X1": 1.0}, "pseudo", "euler", devices=devs, seed=1)     # fewer scenarios than devices
+    assert sum(s.shape[0] for s in tiny) == 2

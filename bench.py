@@ -81,6 +81,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_ready(self, timeout_s: float = 2.0):
+        """nvidia-smi needs 0.1-0.5 s before its first sample: wait for it so the timed region is covered from its start."""
+        t_end = time.perf_counter() + timeout_s
+        while not self.rows and self.proc is not None and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def mark_begin(self):
         """Samples that arrived before this call (warm-up, nvidia-smi start-up) are not part of the timed region."""
         self.t_begin = time.perf_counter()
@@ -203,7 +209,8 @@ def run_gpu(args):
     # ---- device-resident leg: `value`
     sampler = ClockSampler(dev)
     if rank == 0:
-        sampler.start()                                  # nvidia-smi needs ~100 ms to produce its first sample
+        sampler.start()
+        sampler.wait_ready()
     for _ in range(args.warmup):
         plan.run(INIT, N, seed=SEED, scenario_offset=offset, out=out)
     barrier()

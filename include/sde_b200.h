@@ -128,7 +128,8 @@ int sde_plan_create(const sde_universe* u, const char* scheme, const char* rng_m
 void sde_plan_free(sde_plan* p);
 /* Generated CUDA source of the plan (for inspection / offline nvcc + cuobjdump). */
 const char* sde_plan_source(const sde_plan* p);
-/* 0/1: was the cubin found in the ahead-of-time table instead of being NVRTC-compiled? */
+/* 0/1: was the cubin found in the ahead-of-time cache (SDE_B200_CACHE directory, filled by `build()` for the BASELINE
+ * configs and by earlier runs) instead of being NVRTC-compiled at plan creation? */
 int sde_plan_is_prelowered(const sde_plan* p);
 /* Number of elements (f64, or f32 for SDE_DTYPE_F32 paths / terminal values) a run over N scenarios writes. */
 size_t sde_plan_output_elems(const sde_plan* p, uint64_t n_scenarios);

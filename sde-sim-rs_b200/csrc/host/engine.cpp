@@ -144,6 +144,7 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
     const DriverApi& d = driver();
     std::string log;
     std::vector<char> cubin = nvrtc_compile(low_.source, "sde_plan.cu", &log);
+    prelowered_ = log.rfind("(cached on disk", 0) == 0;       // the cubin shipped in the ahead-of-time cache (build/jit_cache)
     cu_check(d.cuModuleLoadData(&mod_, cubin.data()), "cuModuleLoadData(plan)");
     cu_check(d.cuModuleGetFunction(&fn_sim_, mod_, "sde_sim_kernel"), "cuModuleGetFunction(sde_sim_kernel)");
     cu_check(d.cuModuleGetFunction(&fn_fin_, mod_, "sde_moments_finalize"), "cuModuleGetFunction(sde_moments_finalize)");

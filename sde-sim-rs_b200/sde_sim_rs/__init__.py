@@ -148,6 +148,11 @@ class Plan:
     def source(self) -> str:
         return _ffi.lib().sde_plan_source(self._h).decode()
 
+    @property
+    def prelowered(self) -> bool:
+        """True when the cubin came from the ahead-of-time cache on disk instead of an NVRTC compile at plan creation."""
+        return bool(_ffi.lib().sde_plan_is_prelowered(self._h))
+
     def output_shape(self, scenarios: int):
         T, P = self.universe.time_steps.size, self.universe.num_processes
         if self.output == "paths":

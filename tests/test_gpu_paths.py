@@ -429,3 +429,21 @@ def test_simulate_devices_union_equals_single_run():
     assert m[0] == N and abs(m[1] / whole[:, -1, 0].mean() - 1) <= 1e-13
     tiny = S.simulate_devices(GBM_EQ, times, 2, {"X1": 1.0}, "pseudo", "euler", devices=devs, seed=1)     # fewer scenarios than devices
     assert sum(s.shape[0] for s in tiny) == 2
+
+
+def test_ahead_of_time_cache_is_hit_by_a_second_process():
+    # plan creation NVRTC-compiles once per (model, options, headers, NVRTC version) and leaves the cubin in the on-disk cache
+    # (build() fills it for the BASELINE configs); a later process loads it without compiling
+    import os
+    import subprocess
+    import sys
+
+    from conftest import PKG
+
+    code = ("import sde_sim_rs as S; p = S.Plan(S.Universe(['dX1 = ( 0.0123 * X1 ) * dt + ( 0.1717 * X1) * dW1'], "
+            "[k / 7 for k in range(8)]), 'euler', 'pseudo'); print('prelowered', p.prelowered)")
+    env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    first = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    second = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert first.returncode == 0 and second.returncode == 0, first.stderr + second.stderr
+    assert "prelowered True" in second.stdout

@@ -120,7 +120,11 @@ void sde_options_default(sde_options* o);
 
 /* A plan = one model lowered to device code for one (scheme, rng_method, options) choice,
  * compiled for sm_100a, with its direction-number tables resident on the device.
- * Replaces the per-call setup of sim::simulate (src/sim/mod.rs:28-39). */
+ * Replaces the per-call setup of sim::simulate (src/sim/mod.rs:28-39).
+ * Threading: a sde_universe is immutable and may be shared freely (the reference shares &ProcessUniverse across rayon
+ * threads, src/sim/mod.rs:21,45); a sde_plan owns scratch buffers (moment partials, chunk buffers, digital-shift masks), so
+ * its runs must be serialised — one stream at a time per plan; create one plan per thread / stream for concurrent work.
+ * sde_simulate builds its own plan per call and is re-entrant. */
 typedef struct sde_plan sde_plan;
 
 int sde_plan_create(const sde_universe* u, const char* scheme, const char* rng_method,

@@ -166,6 +166,39 @@ __device__ __forceinline__ double sde_icdf_normal_fast_j53(sde_u64 j, const doub
     return __hiloint2double(xhi, __double2loint(x));
 }
 
+// Same map from the two raw 32-bit words of a u64 draw (rand: f64 = (u64 >> 11) * 2^-53), bit-identical to the j53 entry
+// whenever min(p, 1-p) >= 2^-32 — all but 2^-32 of the draws.  X = u64 with its low 11 bits cleared is j 2^11, so
+// p = X 2^-64 and min(p, 1-p) 2^64 is X or its two's complement -X; with a non-zero high word the leading one, the 52
+// mantissa bits and the exponent come from one FLO and three funnel shifts on 32-bit words instead of 64-bit compare /
+// select / shift sequences: ~16 integer instructions instead of ~26 (the ChaCha-driven modes are bound by the integer ALU
+// pipe).  Branch-free: `*xh_out` receives the high word of the folded value; when it is zero (w < 2^-32, or p = 0) the
+// returned value is meaningless and the caller must redo the draw through sde_icdf_normal_fast_j53 — the fused kernel
+// does that once per step group, outside the straight-line draw code.
+__device__ __forceinline__ double sde_icdf_normal_fast_w64(sde_u32 lo, sde_u32 hi, const double* s_table, int lane, sde_u32* xh_out) {
+    const int sgn = (int)hi >> 31;                           // all ones when p >= 0.5
+    const sde_u64 xs = ((sde_u64)(hi ^ (sde_u32)sgn) << 32) | (sde_u64)((lo & 0xfffff800u) ^ (sde_u32)sgn);
+    const sde_u64 xf = xs + (sde_u64)(sde_u32)(-sgn);        // (X ^ S) - S: conditional 64-bit negate
+    const sde_u32 xl = (sde_u32)xf, xh = (sde_u32)(xf >> 32);
+    *xh_out = xh;
+    int pos;                                                  // leading one of the high word: w = 1.m * 2^(pos - 32)
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(xh));
+    const int sh = 31 - pos;
+    const sde_u32 nh = __funnelshift_l(xl, xh, sh);          // normalised: leading one at bit 31 of nh
+    const sde_u32 nl = xl << (sh & 31);
+    const sde_u32 mb_hi = (nh & 0x7fffffffu) >> 11;          // 20 + 32 mantissa bits below the leading one (exact: X is a
+    const sde_u32 mb_lo = __funnelshift_l(nl, nh, 21);       // multiple of 2^11, nothing is shifted out)
+    double x = sde_icdf_as_core(mb_hi, mb_lo, s_table + SDE_ICDF_LOG_DOUBLES + 21 + (pos & 31),   // h - 53 = pos - 32
+                                s_table + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
+    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                          // p < 0.5 -> -x
+    return __hiloint2double(xhi, __double2loint(x));
+}
+// high word of the folded value for the raw words of a draw (the rare-path test of the caller)
+__device__ __forceinline__ sde_u32 sde_icdf_w64_folded_high(sde_u32 lo, sde_u32 hi) {
+    const int sgn = (int)hi >> 31;
+    const sde_u64 xs = ((sde_u64)(hi ^ (sde_u32)sgn) << 32) | (sde_u64)((lo & 0xfffff800u) ^ (sde_u32)sgn);
+    return (sde_u32)((xs + (sde_u64)(sde_u32)(-sgn)) >> 32);
+}
+
 // p = (k + 1/2) * 2^-32, k = 32-bit digitally shifted Sobol integer: p = (2k+1) * 2^-33.
 // 1 - p = (2 ~k + 1) * 2^-33, so min(p, 1-p) is a conditional bit flip of k.
 __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const double* s_table, int lane) {

@@ -45,6 +45,9 @@
 #pragma once
 #include "sde_sim_common.cuh"
 
+#ifndef SDE_W64_RARE_SHIFT
+#define SDE_W64_RARE_SHIFT 0   /* test hook: > 0 sends draws with min(p, 1-p) < 2^(shift-32) through the rare path as well */
+#endif
 #define SDE_NW (SDE_BLOCK / 32)
 #define SDE_USES_CHACHA (SDE_RNG == 0 || SDE_RNG == 1)
 #define SDE_USES_SOBOL (SDE_RNG == 1 || SDE_RNG == 2 || SDE_RNG == 3)
@@ -232,6 +235,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     SdeChaCha8Stream cha;
     cha.init(prm.seed + s_global);                                 // sim/mod.rs:56,65 (wrapping add)
 #endif
+    sde_u32 rare_min = 0xffffffffu;                                // see draw_fixup
+    (void)rare_min;
 
 #if SDE_OUT == 0
     if (valid) {
@@ -308,7 +313,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 if (k == 0 && SDE_NEEDS_U0) u0 = (double)(long long)jc * 1.1102230246251565e-16;
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
-                    zu[k] = sde_icdf_normal_fast_j53(jc, s_icdf, lane);
+                    {
+                        sde_u32 xh;
+                        zu[k] = sde_icdf_normal_fast_w64(cha.buf[2 * slot], cha.buf[2 * slot + 1], s_icdf, lane, &xh);
+                        rare_min = min(rare_min, xh >> SDE_W64_RARE_SHIFT);   // 0 marks a draw with min(p, 1-p) < 2^-32: redone in draw_fixup
+                    }
 #elif SDE_ICDF == 2
                     zu[k] = sde_icdf_normal_single((double)(long long)jc * 1.1102230246251565e-16);
 #else
@@ -347,6 +356,31 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #endif
         };
+#if SDE_RNG == 0 && SDE_ICDF == 1
+        // Rare path of the 32-bit-word inverse normal (sde_icdf_normal_fast_w64): when some draw of the last `ns` steps had
+        // min(p, 1-p) < 2^-32 (once per 2^32 draws) its block is regenerated (ChaCha is counter based) and the draw redone through
+        // the general 53-bit entry.  One cold branch per step group keeps the draw code itself straight-line.
+        auto draw_fixup = [&](const int tc, const int ns, sde_real (*zu)[SDE_KK]) __attribute__((always_inline)) {
+            if (__builtin_expect(rare_min == 0u, 0)) {
+                for (int j = 0; j < ns; ++j)
+                    for (int k = 0; k < SDE_K; ++k) {
+                        if (!sde_factor_is_wiener(k)) continue;
+                        const sde_u64 i = (sde_u64)(tc + j) * SDE_K + k;                 // draw index in the path's stream
+                        sde_u32 blk[16];
+                        sde_chacha_block<8>(cha.key, i >> 3, blk);
+                        const int s2 = 2 * (int)(i & 7);
+                        sde_u32 lo = 0, hi = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (s2 == 2 * q) { lo = blk[2 * q]; hi = blk[2 * q + 1]; }
+                        if ((sde_icdf_w64_folded_high(lo, hi) >> SDE_W64_RARE_SHIFT) == 0u)
+                            zu[j][k] = sde_icdf_normal_fast_j53((((sde_u64)hi << 32) | (sde_u64)lo) >> 11, s_icdf, lane);
+                    }
+            }
+            rare_min = 0xffffffffu;
+        };
+#else
+        auto draw_fixup = [&](const int, const int, sde_real (*)[SDE_KK]) __attribute__((always_inline)) {};
+#endif
         auto advance = [&](const int t, const sde_real (&zu)[SDE_KK], const sde_real u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
@@ -368,6 +402,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             sde_real zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
+            draw_fixup(tc, SDE_UNR, zu);
 #if SDE_DIRECT
             sde_real vals[SDE_UNR * SDE_P];                     // rows tc+1 .. tc+4, in output order
 #pragma unroll
@@ -401,9 +436,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
         // one step on its own (ragged ends); direct mode stores its row element-wise
         auto single = [&](const int t, const int j) __attribute__((always_inline)) {
-            sde_real zu[SDE_KK], u0;
-            draw(t, j, zu, u0);
-            advance(t, zu, u0);
+            sde_real zu[1][SDE_KK], u0;
+            draw(t, j, zu[0], u0);
+            draw_fixup(t, 1, zu);
+            advance(t, zu[0], u0);
 #if SDE_DIRECT
             if (valid) {
 #pragma unroll

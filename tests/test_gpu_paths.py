@@ -447,3 +447,20 @@ def test_ahead_of_time_cache_is_hit_by_a_second_process():
     second = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert first.returncode == 0 and second.returncode == 0, first.stderr + second.stderr
     assert "prelowered True" in second.stdout
+
+
+def test_pseudo_inverse_normal_rare_path_is_bit_identical(monkeypatch):
+    # The ChaCha-driven fast tier evaluates the inverse normal from the two 32-bit words of a draw and redoes the draws with
+    # min(p, 1-p) < 2^-32 (one in 2^32) through the general 53-bit entry in a per-group fix-up.  The test hook widens "rare" to
+    # min(p, 1-p) < 2^-8, so thousands of draws take the fix-up (block regenerated from the counter, slot picked, draw replaced):
+    # the results must not change by a single bit, for one factor, two factors (Heston) and a step count that leaves single steps.
+    cases = [(GBM_EQ, {"X1": 1.0}, "euler", grid(365, 37)), (HESTON_EQ, {"S": 100.0, "v": 0.04}, "runge-kutta", grid(1000, 23))]
+    for eqs, init, scheme, times in cases:
+        kw = dict(icdf="fast", arithmetic="fast")
+        monkeypatch.delenv("SDE_B200_DEFINES", raising=False)
+        base = S.Plan(S.Universe(eqs, times), scheme, "pseudo", **kw).run(init, 3000, seed=11).cpu().numpy()
+        monkeypatch.setenv("SDE_B200_DEFINES", "SDE_W64_RARE_SHIFT=24")
+        hooked = S.Plan(S.Universe(eqs, times), scheme, "pseudo", **kw)
+        assert "#define SDE_W64_RARE_SHIFT 24" in hooked.source
+        assert np.array_equal(hooked.run(init, 3000, seed=11).cpu().numpy(), base)
+    monkeypatch.delenv("SDE_B200_DEFINES", raising=False)

@@ -268,6 +268,8 @@ class StepGen {
     void runge_kutta() {                                     // src/sim/runge_kutta.rs:5-107
         const int P = u_.P();
         line("const sde_real sk = (u0 > " + format_real(0.5) + ") ? " + format_real(1.0) + " : " + format_real(-1.0) + ";   // runge_kutta.rs:18-22");
+        // arithmetic=fast: the probe perturbation c * sk * sqrt(dt) shares one product sk * sqrt(dt) per step (<= 1 ulp per term)
+        if (!opt_.strict) line("const sde_real sksq = sk * sqrt_dt;");
         if (opt_.rk_textbook) state_ = OLD;                  // textbook variant: k1 at the settled row
         for (int p = 0; p < P; ++p) {                        // :26-35 pre-sample, reused by k1 and k2
             const Process& pr = u_.processes[p];
@@ -296,7 +298,7 @@ class StepGen {
             for (const Term& t : pr.terms) {
                 if (t.kind != IncKind::Wiener) continue;
                 std::string cf = eval(t.coeff, CUR);
-                line("  pert = " + add("pert", mul(mul(cf, "sk"), "sqrt_dt")) + ";");
+                line("  pert = " + add("pert", opt_.strict ? mul(mul(cf, "sk"), "sqrt_dt") : mul(cf, "sksq")) + ";");
             }
             line("  n" + sp + " = " + add(add("x" + sp, "k1_" + sp), "pert") + "; }");
         }

@@ -426,7 +426,8 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     if (gen.matrix && opt.wide_mma != 0 && opt.rng == RNG_SOBOL_XOR && opt.out != OUT_PATHS_TPN && !opt.f32) {
         const int NB = (P + 7) / 8, NKK = (K + 3) / 4, S = u.T() - 1;
         const int per_tile = 2 * NB + NKK;
-        const int mt = 2 * per_tile <= 64 ? 2 : (per_tile <= 64 ? 1 : 0);
+        int mt = 2 * per_tile <= 64 ? 2 : (per_tile <= 64 ? 1 : 0);
+        if (const char* g = std::getenv("SDE_B200_WIDE_MT")) mt = std::min(mt, std::max(1, std::atoi(g)));   // tuning
         // measured on B200 (64 assets, tools/run_c4.py): 16 warps per SM at a 128-register cap (a few hundred bytes of
         // L1-resident spills) beat 8 warps at 255 registers, 3.72 vs 3.47 G path-steps/s — the dependent DMMA chains
         // and the 19-deep inverse-normal chains want the extra warps more than the registers

@@ -3,9 +3,8 @@
 // Same contract as sde_sim_kernel.cuh (one launch = the parallel region of sim::simulate, src/sim/mod.rs:41-88),
 // selected by the lowering when the model is a Cholesky-loaded basket — every process Levy with coefficients
 // a_j X_i on dt / dW_k only (src/sim/euler.rs:15-28 applied to `( a * S_i ) * dW_k` terms) — driven by scrambled
-// Sobol points (BASELINE config C4: 64 assets, 64 factors, terminal moments; full paths in reference order and terminal
-// values as well).  One Euler
-// step of such a model is
+// Sobol points: BASELINE config C4 (64 assets, 64 factors, terminal moments), and the same models with terminal values
+// or full paths in reference order.  One Euler step of such a model is
 //     X_i <- X_i * (1 + a_i dt + sqrt(dt) * sum_k M[i][k] z_k),
 // i.e. per step a [paths x K] * [K x P] matrix product in f64: GEMM-shaped work, so it runs on the FP64 tensor
 // path (DMMA, mma.sync.m8n8k4.f64) instead of P*K scalar FMAs per path with one constant-memory operand each.

@@ -13,6 +13,7 @@
 //   * ChaCha: `cryptography` ChaCha20 keystream (r=20) + rand_chacha's own KAT          (tests/test_oracle_chacha.py)
 //   * icdf / Poisson: known answers computed with glibc (same libm Rust links to)        (tests/test_oracle_icdf.py)
 //   * schemes: an independent pure-Python restatement (oracle/py_restatement.py)         (tests/test_oracle_schemes.py)
+//   * committed fixtures: the independent pins above + frozen outputs per BASELINE config (tests/golden/, tests/test_golden.py)
 // Two declared deviations from the reference: an explicit `seed` replaces
 // rand::rng().random() (src/sim/mod.rs:28-29) and the Sobol point of scenario s is
 // n = s + 5 (the single-thread order) instead of the Mutex race (src/sim/mod.rs:36-64).

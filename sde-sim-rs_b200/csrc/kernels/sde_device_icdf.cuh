@@ -89,7 +89,27 @@ __constant__ double sde_kc[12] = {
     0.375,                                 // 8   3/8 of the cubic square-root step
     -2.772588722239781,                    // 9   -4 ln 2: exponent term, D = 32 + pos/2 variant
     -1.3862943611198906,                   // 10  -2 ln 2: exponent term, converted-integer variant
-    -0.6666666666666666};                  // 11  -2/3: cubic Taylor term of the wide-table logarithm
+    -0.6666666666666666};
+// SDE_KC(i): coefficient i of the FAST path.  Default: the __constant__ array above.  SDE_KC_LITERAL (tuning only): the same values
+// as literals, which ptxas places on uniform-register operands more often (operand forms).
+#ifdef SDE_KC_LITERAL
+#define SDE_KCL_0 (0x1.0000999a03338p-1)
+#define SDE_KCL_1 (-0x1.55560888fbbc1p-1)
+#define SDE_KCL_2 (SDE_AS_C2)
+#define SDE_KCL_3 (SDE_AS_C1)
+#define SDE_KCL_4 (SDE_AS_C0)
+#define SDE_KCL_5 (SDE_AS_D3)
+#define SDE_KCL_6 (SDE_AS_D2)
+#define SDE_KCL_7 (SDE_AS_D1)
+#define SDE_KCL_8 (0.375)
+#define SDE_KCL_9 (-2.772588722239781)
+#define SDE_KCL_10 (-1.3862943611198906)
+#define SDE_KCL_11 (-0.6666666666666666)
+#define SDE_KC(i) SDE_KCL_##i
+#else
+#define SDE_KC(i) sde_kc[i]
+#endif
+                  // 11  -2/3: cubic Taylor term of the wide-table logarithm
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
@@ -116,7 +136,7 @@ __constant__ double sde_kc[12] = {
 __device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double d1, const double d2);
 __device__ __forceinline__ double sde_icdf_as_core_b(const double m, const double2 tc, const double base) {
     const double r = fma(m, tc.x, -1.0);
-    double q = fma(r, sde_kc[0], sde_kc[1]);
+    double q = fma(r, SDE_KC(0), SDE_KC(1));
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
     return sde_icdf_as_tail(fma(q, r, base), tc.x, base);
@@ -126,14 +146,14 @@ __device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double
     const double y0 = SDE_SEED_LOW(sde_rsqrt_approx(w2), d1);
     const double g = w2 * y0;
     const double e2 = fma(-g, y0, 1.0);
-    const double ps = fma(e2, sde_kc[8], 0.5);
+    const double ps = fma(e2, SDE_KC(8), 0.5);
     const double t = fma(g, e2 * ps, g);
     // N(t) = (c0 + c2 w2) + c1 t and D(t) = (1 + d2 w2) + t (d1 + d3 w2): t^2 = w2 is known before the square root
     // is, so only one FMA of each polynomial waits for t (same operation count as Horner, shorter critical path)
-    const double ne = fma(sde_kc[2], w2, sde_kc[4]);
-    const double de = fma(sde_kc[6], w2, 1.0);
-    const double dd = fma(sde_kc[5], w2, sde_kc[7]);
-    const double num = fma(sde_kc[3], t, ne);
+    const double ne = fma(SDE_KC(2), w2, SDE_KC(4));
+    const double de = fma(SDE_KC(6), w2, 1.0);
+    const double dd = fma(SDE_KC(5), w2, SDE_KC(7));
+    const double num = fma(SDE_KC(3), t, ne);
     const double den = fma(t, dd, de);
     // x = t - N/D with 1/D = r0 (1 + ed + ed^2), ed = 1 - D r0 (cubic step on the MUFU seed), folded into one final FMA
     const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), d2);
@@ -235,9 +255,9 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 t
 #if SDE_ICDF_EXP_MAGIC
     sde_u32 dh;
     asm("mad.lo.u32 %0, %1, 16384, 0x40400000;" : "=r"(dh) : "r"((sde_u32)pos));
-    const double base = fma(__hiloint2double((int)dh, 0), sde_kc[9], tc.y);
+    const double base = fma(__hiloint2double((int)dh, 0), SDE_KC(9), tc.y);
 #else
-    const double base = fma((double)pos, sde_kc[10], tc.y);
+    const double base = fma((double)pos, SDE_KC(10), tc.y);
 #endif
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double x = sde_icdf_as_core_b(m, tc, base);
@@ -271,10 +291,10 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32w(sde_u32 k, sde_u32 t
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(mh >> (32 - SDE_ICDF_WIDE_BITS)), "r"(16u * SDE_ICDF_TABLE_REPL), "r"(tab_lane));
     double2 tc;                                              // {1/c, -2 ln c + 66 ln 2}
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc.x), "=d"(tc.y) : "r"(ta));
-    const double base = fma((double)pos, sde_kc[10], tc.y);
+    const double base = fma((double)pos, SDE_KC(10), tc.y);
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double r = fma(m, tc.x, -1.0);
-    double q = fma(r, sde_kc[11], 1.0);                      // -2 log1p(r) = r (-2 + r (1 - 2/3 r)) + O(r^4 / 2)
+    double q = fma(r, SDE_KC(11), 1.0);                      // -2 log1p(r) = r (-2 + r (1 - 2/3 r)) + O(r^4 / 2)
     q = fma(q, r, -2.0);
     const double x = sde_icdf_as_tail(fma(q, r, base), tc.x, base);
     const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x

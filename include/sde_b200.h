@@ -97,7 +97,8 @@ typedef struct sde_options {
     int32_t icdf;             /* enum sde_icdf                                                      */
     int32_t arith;            /* enum sde_arith                                                     */
     int32_t rk_variant;       /* enum sde_rk_variant                                                */
-    void* stream;             /* CUstream to launch on (NULL = library-owned stream)                */
+    void* stream;             /* sde_simulate only: CUstream to launch on (NULL = a library-owned stream); the call waits for
+                               * the result either way.  Plans take their stream per run (sde_plan_run_device)        */
     const double* inject;     /* DEVICE pointer [N][S][K+1] or NULL.  Test hook for the "identical normal draws" parity check:
                                  entry k<K is the normal z (Wiener factor) or uniform u (Poisson factor) of factor k, entry K is u[t][0] (RK's sk). */
     int32_t tile_steps;       /* 0 = auto; time-tile length override (tuning)                       */
@@ -146,7 +147,8 @@ int sde_lower_only(const sde_universe* u, const char* scheme, const char* rng_me
 void sde_free_string(char* s);
 
 /* Run N scenarios; result written to DEVICE memory `d_out` (caller-owned, e.g. a torch
- * tensor).  Asynchronous on opt.stream.  seed / scenario_offset may differ per run.
+ * tensor).  Asynchronous on `stream` (a CUstream; NULL = the legacy default stream, so the launch is ordered with the
+ * caller's default-stream work and nothing is synchronised).  seed / scenario_offset may differ per run.
  * For SDE_OUT_MOMENTS d_out receives [P][3] (count, mean, M2).  kernel launches are
  * counted in *n_launches when non-NULL. */
 int sde_plan_run_device(sde_plan* p, const char* const* init_names, const double* init_vals,

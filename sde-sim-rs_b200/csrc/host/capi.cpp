@@ -205,8 +205,8 @@ int sde_simulate(const sde_universe* u, const char* const* init_names, const dou
         r->elems = r->plan->output_elems(n_scenarios);
         use_device(po.device);
         r->values.alloc(r->plan->output_bytes(n_scenarios));
-        r->plan->run_device(init_pairs(init_names, init_vals, n_init), n_scenarios, o.seed, o.scenario_offset,
-                            r->values.as<double>(), o.inject, nullptr, nullptr);
+        r->plan->run_timed(init_pairs(init_names, init_vals, n_init), n_scenarios, o.seed, o.scenario_offset,
+                           r->values.as<double>(), o.inject, (CUstream)o.stream, nullptr);
         r->kernel_ms = r->plan->last_kernel_ms();
         *out = r.release();
     });

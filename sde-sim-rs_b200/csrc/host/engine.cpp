@@ -315,21 +315,31 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
 
 void Plan::run_device(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
                       uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches) {
+    // asynchronous on `stream`; nullptr is the legacy default stream (what torch.cuda.current_stream().cuda_stream is
+    // unless the caller switched streams), so the launch is ordered with the caller's pending work on it
+    use_device(opt_.device);
+    if (opt_.lower.rng == RNG_INJECT && !d_inject) throw ExprError{"injected-draw plan needs options.inject"};
+    set_initial_values(init, stream);
+    ensure_masks(seed, stream);
+    launch(n, seed, scenario_offset, d_out, d_inject, stream, n_launches);
+}
+
+void Plan::run_timed(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
+                     uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches) {
+    // synchronous: launches on `stream` (nullptr = the plan's own stream), waits, records the kernel time
     use_device(opt_.device);
     if (opt_.lower.rng == RNG_INJECT && !d_inject) throw ExprError{"injected-draw plan needs options.inject"};
     CUstream s = stream ? stream : own_stream_;
     set_initial_values(init, s);
     ensure_masks(seed, s);
     const DriverApi& d = driver();
-    if (!stream) cu_check(d.cuEventRecord(ev_a_, s), "cuEventRecord");
+    cu_check(d.cuEventRecord(ev_a_, s), "cuEventRecord");
     launch(n, seed, scenario_offset, d_out, d_inject, s, n_launches);
-    if (!stream) {
-        cu_check(d.cuEventRecord(ev_b_, s), "cuEventRecord");
-        cu_check(d.cuStreamSynchronize(s), "cuStreamSynchronize");
-        float ms = 0;
-        d.cuEventElapsedTime(&ms, ev_a_, ev_b_);
-        last_ms_ = ms;
-    }
+    cu_check(d.cuEventRecord(ev_b_, s), "cuEventRecord");
+    cu_check(d.cuStreamSynchronize(s), "cuStreamSynchronize");
+    float ms = 0;
+    d.cuEventElapsedTime(&ms, ev_a_, ev_b_);
+    last_ms_ = ms;
 }
 
 void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,

@@ -43,9 +43,12 @@ class Plan {
     size_t elem_bytes() const { return opt_.lower.f32 ? 4 : 8; }
     size_t output_bytes(uint64_t n) const { return output_elems(n) * (opt_.lower.out == OUT_MOMENTS ? 8 : elem_bytes()); }
 
-    // Asynchronous on `stream` (nullptr = the plan's own stream, then synchronised before return).
+    // Asynchronous on `stream` (nullptr = the legacy default stream).
     void run_device(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
                     uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches);
+    // Synchronous on `stream` (nullptr = the plan's own stream): waits for the result and records last_kernel_ms().
+    void run_timed(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
+                   uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches);
     void run_host(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed,
                   uint64_t scenario_offset, double* h_out, int* n_launches);
     double last_kernel_ms() const { return last_ms_; }

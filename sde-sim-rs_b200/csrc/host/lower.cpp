@@ -382,6 +382,10 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     const int nslot = (int)table_slots.size();
 
     // ---- launch shape
+    // every kernel decomposes the Sobol index as CTA part ^ warp part ^ lane part and sizes shared arrays per warp:
+    // a CTA is a whole number of warps, at most 1024 threads
+    if (opt.block != 0 && (opt.block < 32 || opt.block > 1024 || opt.block % 32 != 0))
+        throw ExprError{"block_threads must be 0 (auto) or a multiple of 32 in [32, 1024], got " + std::to_string(opt.block)};
     L.block = opt.block > 0 ? opt.block : 256;
     // steps unrolled per loop trip: whole ChaCha blocks, and >= 4 for small models so that loads, constants and
     // the state-independent inverse-CDF chains of neighbouring steps overlap

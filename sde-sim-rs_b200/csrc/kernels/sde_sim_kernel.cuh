@@ -267,6 +267,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     }
     __syncthreads();
 
+#if SDE_DIRECT
+    // next of the <= 3 steps that follow the warp's last full group; they run in whichever tile stages them (-1: not yet known)
+    int tail_t = -1;
+#endif
     int buf = 0;
     for (int t0 = 0; t0 < S; t0 += SDE_TT, buf ^= 1) {
         const int t_end = min(t0 + SDE_TT, S);
@@ -468,9 +472,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += 4) group(tc);
             if (more) issue(t0 + SDE_TT, pf);
             if (n_groups > 0) { group(tc); tc += 4; }
-            if (!more) {
+            // The <= 3 steps after the last full group run as soon as the groups are done, in the tile whose staged tables
+            // [t0, t0 + SDE_TS) hold them.  (The last group can end up to 3 steps before a tile boundary; left to the last
+            // tile, a tail that starts before that tile's t0 would index its staged tables with negative offsets.)
+            if (t0 + SDE_TT + g_eff >= s_full) {
+                if (tail_t < 0) tail_t = s_full;              // first such tile: t0 + g_eff < s_full held in the tile before
+                const int staged_end = min(t0 + SDE_TS, S);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) if (s_full + j < S) single(s_full + j, j);
+                for (int j = 0; j < 3; ++j)
+                    if (tail_t < staged_end) { single(tail_t, j); ++tail_t; }
             }
         }
 #else

@@ -414,9 +414,22 @@ def simulate_sharded(processes_equations, time_steps, scenarios, initial_values,
     import torch.distributed as dist
 
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
+        raise ValueError("scenarios must be a positive integer")                      # every rank raises: no collective entered
     lo, hi = shard_range(scenarios, rank, world)
-    res = simulate(processes_equations, time_steps, hi - lo, initial_values, rng_method, scheme, seed=seed,
-                   output=output, scenario_offset=lo, **kw)
+    if hi > lo:
+        res = simulate(processes_equations, time_steps, hi - lo, initial_values, rng_method, scheme, seed=seed,
+                       output=output, scenario_offset=lo, **kw)
+    else:
+        # fewer scenarios than ranks: this rank owns none, but it still enters the collective with a zero-count triple
+        uni = Universe(list(processes_equations), time_steps)
+        T, P = uni.time_steps.size, uni.num_processes
+        shape = {"moments": (P, 3), "terminal": (0, P)}.get(output, (0, T, P) if kw.get("layout", "NTP") == "NTP" else (T, P, 0))
+        dev = kw.get("device")
+        dev = _current_device() if dev is None else int(dev)
+        dt = torch.float32 if (kw.get("dtype", "f64") in ("f32", "float32") and output != "moments") else torch.float64
+        res = Filtration(torch.zeros(shape, dtype=dt, device=f"cuda:{dev}" if torch.cuda.is_available() else "cpu"),
+                         uni.time_steps, uni.process_names, output=output, layout=kw.get("layout", "NTP"), scenario_offset=lo, seed=seed)
     if output == "moments" and world > 1:
         gathered = [torch.empty_like(res.values) for _ in range(world)]
         dist.all_gather(gathered, res.values)

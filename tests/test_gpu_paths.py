@@ -347,6 +347,26 @@ def test_ragged_step_counts_all_store_paths(oracle, steps):
             assert rel_err(got, ref) <= 1e-12, (steps, direct, len(eqs), rel_err(got, ref))
 
 
+@pytest.mark.parametrize("steps", [33, 34, 65, 66, 97, 98, 130])
+def test_last_tile_of_one_or_two_steps(oracle, steps):
+    # time-tiled kernel with direct sector stores: a last tile of 1-2 steps while a warp's last full group ended before the
+    # tile boundary (S mod TT in {1, 2}; tile_steps=32 pins TT): the <= 3 trailing steps must read the tile that stages them.
+    # Both users of that kernel: Sobol plans (ntp_direct=2) and injected draws; scenario offsets cover all four gammas.
+    times = grid(252, steps)
+    U = oracle.Universe(GBM_EQ, times)
+    for off in (0, 1, 2, 3):
+        ref = oracle.simulate(U, {"X1": 1.0}, 700, "euler", "sobol", seed=3, scramble="xor", scenario_offset=off)
+        for tt in (0, 32):
+            plan = S.Plan(S.Universe(GBM_EQ, times), "euler", "sobol", scramble="xor", ntp_direct=2, tile_steps=tt)
+            got = plan.run({"X1": 1.0}, 700, seed=3, scenario_offset=off).cpu().numpy()
+            assert rel_err(got, ref) <= 1e-12, (steps, off, tt, rel_err(got, ref))
+    inj = _inject(oracle, U, 700, "pseudo", 11, [True])
+    ref = oracle.simulate(U, {"X1": 1.0}, 700, "euler", inject=inj)
+    for tt in (0, 32):
+        plan = S.Plan(S.Universe(GBM_EQ, times), "euler", "pseudo", inject=torch.from_numpy(inj).cuda(), tile_steps=tt)
+        assert rel_err(plan.run({"X1": 1.0}, 700).cpu().numpy(), ref) <= 1e-12, (steps, tt)
+
+
 @pytest.mark.parametrize("N,off", [(1, 0), (2, 3), (5, 250), (251, 5), (256, 251), (257, 0), (1000, 4091)])
 def test_ragged_scenario_counts_and_offsets(oracle, N, off):
     times = grid(252, 41)

@@ -85,7 +85,8 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"),
-                        ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"), wide_mma=kw.get("wide_mma", 0))
+                        ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"), wide_mma=kw.get("wide_mma", 0),
+                        block_threads=kw.get("block_threads", 0), tile_steps=kw.get("tile_steps", 0))
     src, nb = C.c_void_p(), C.c_size_t(0)
     rc = _ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), compile, C.byref(src), C.byref(nb))
     _ffi.check(rc)
@@ -107,6 +108,49 @@ def test_f32_needs_fast_arithmetic_and_emits_float_literals():
     assert "0.05 " not in text.split("sde_model_step(")[1]             # no f64 literal inside the model step
     text64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, arithmetic="fast")
     assert "SDE_F32" not in text64 and "0.050000000000000003" in text64
+
+
+@pytest.mark.parametrize("block", [16, 100, 160 + 1, 2048, -32])
+def test_block_threads_must_be_whole_warps(block):
+    # every kernel splits the Sobol index into CTA ^ warp ^ lane parts and sizes shared arrays per warp
+    for kw in (dict(), dict(scramble="xor", ntp_direct=2), dict(scramble="xor", ntp_direct=3)):
+        with pytest.raises(ValueError, match="block_threads must be"):
+            _lower(GBM_EQ, grid(252, 40), "euler", "sobol", compile=0, block_threads=block, **kw)
+    _lower(GBM_EQ, grid(252, 40), "euler", "sobol", compile=0, block_threads=160, scramble="xor", ntp_direct=2)
+
+
+def test_direct_store_tile_walk_visits_every_step_once_inside_its_tile():
+    """Host-side emulation of the step schedule of sde_sim_kernel.cuh with SDE_DIRECT (same expressions as the kernel):
+    per warp, gamma head steps, 4-step groups shifted by gamma across tiles of TT steps, then <= 3 trailing steps.  Every
+    step must run exactly once, in order, and inside the window [t0, t0 + TT + 3) that its tile stages in shared memory."""
+    for TT in (4, 16, 32, 36):
+        TS = TT + 3
+        for S_ in list(range(1, 150)) + [252, 1000, 2017, 2018, 2049, 2050]:
+            for gamma in range(4):
+                seen, tail_t = [], -1
+                g_eff = min(gamma, S_)
+                s_full = g_eff + ((S_ - g_eff) & ~3)
+                for t0 in range(0, S_, TT):
+                    staged = range(t0, min(t0 + TS, S_))
+                    run = []
+                    if t0 == 0:
+                        run += [j for j in range(3) if j < g_eff]
+                    tc = t0 + g_eff
+                    t_hi = min(t0 + TT + g_eff, s_full)
+                    n_groups = (t_hi - tc) >> 2 if t_hi > tc else 0
+                    for _ in range(n_groups):
+                        run += [tc, tc + 1, tc + 2, tc + 3]
+                        tc += 4
+                    if t0 + TT + g_eff >= s_full:
+                        if tail_t < 0:
+                            tail_t = s_full
+                        for _ in range(3):
+                            if tail_t < min(t0 + TS, S_):
+                                run.append(tail_t)
+                                tail_t += 1
+                    assert all(t in staged for t in run), (TT, S_, gamma, t0, run)
+                    seen += run
+                assert seen == list(range(S_)), (TT, S_, gamma)
 
 
 def test_rk_without_factor_is_value_error():

@@ -178,6 +178,44 @@ size_t sde_result_num_elems(const sde_result* r);
 const double* sde_result_values_device(const sde_result* r);
 int sde_result_values_host(const sde_result* r, double* dst, size_t n_elems);   /* the `value` column, filtration.rs:112 */
 double sde_result_kernel_ms(const sde_result* r);
+/* What the reference's frame carries besides `value` (src/filtration.rs:108-113): the process names in equation order
+ * (`process_name`, src/proc/mod.rs:75-76), the time grid (`time`) and the global index of the first scenario (`scenario`). */
+const char* sde_result_process_name(const sde_result* r, size_t i);
+int sde_result_times(const sde_result* r, double* dst, size_t n_times);
+uint64_t sde_result_scenario_offset(const sde_result* r);
+int sde_result_device(const sde_result* r);
+int sde_result_output(const sde_result* r);                  /* enum sde_output */
+/* SDE_OUT_MOMENTS results: the [P][3] (count, mean, M2) triples, host copy. */
+int sde_result_moments(const sde_result* r, double* dst);
+
+/* ---- several GPUs of one box, one host thread -------------------------------------------
+ * Replaces the rayon `into_par_iter` over scenarios inside sim::simulate (src/sim/mod.rs:41-43,88): device i of G
+ * simulates the scenarios sde_shard_range(N, i, G) — disjoint Sobol index ranges / ChaCha keys, so the union of the
+ * shards is bit-identical to a one-device run — and every launch is issued before any device is synchronised.
+ * SDE_OUT_MOMENTS: every device reduces its shard; the 3 P doubles per device are all-gathered over NCCL
+ * (ncclAllGather inside one group on the compute streams; libnccl.so.2 is dlopen'ed, peer-to-peer copies stand in when
+ * it is absent) and Chan-merged by a device kernel right behind, so every device holds the merged [P][3].  No host hop. */
+typedef struct sde_device_plans sde_device_plans;
+void sde_shard_range(uint64_t n_scenarios, size_t part, size_t n_parts, uint64_t* lo, uint64_t* hi);
+/* One plan per device of `devices` (NULL: every visible device) + the communicator the moment merge needs. */
+int sde_device_plans_create(const sde_universe* u, const char* scheme, const char* rng_method, const sde_options* opt,
+                            const int32_t* devices, size_t n_devices, sde_device_plans** out);
+void sde_device_plans_free(sde_device_plans* ps);
+size_t sde_device_plans_count(const sde_device_plans* ps);
+int sde_device_plans_device(const sde_device_plans* ps, size_t i);
+int sde_device_plans_collective(const sde_device_plans* ps);  /* 0 none (one device / no moments), 1 NCCL, 2 peer-to-peer copies */
+/* d_out[i]: DEVICE memory on device i receiving shard i ([n_i][T][P] paths / [n_i][P] terminal values) or, for
+ * SDE_OUT_MOMENTS, the merged [P][3] (NULL entries are skipped for moments).  Synchronous.  collective_ms (optional):
+ * device time from the first gather call to the end of the merge kernel on device 0. */
+int sde_plan_run_devices(sde_device_plans* ps, const char* const* init_names, const double* init_vals, size_t n_init,
+                         uint64_t n_scenarios, uint64_t seed, uint64_t scenario_offset, double* const* d_out,
+                         int* n_launches, double* collective_ms);
+/* sim::simulate over several devices in one call: out[i] receives shard i (sde_result_scenario_offset / _shape tell
+ * which scenarios; for SDE_OUT_MOMENTS every out[i] holds the merged triples).  `out` has room for n_devices results
+ * (the number of visible devices when `devices` is NULL). */
+int sde_simulate_devices(const sde_universe* u, const char* const* init_names, const double* init_vals, size_t n_init,
+                         uint64_t n_scenarios, const char* scheme, const char* rng_method, const sde_options* opt,
+                         const int32_t* devices, size_t n_devices, sde_result** out);
 
 /* ---- building blocks exposed for parity tests and measurement ------------------------- */
 
@@ -195,6 +233,9 @@ int sde_icdf_normal(int device, int mode, const double* h_p, size_t n, double* h
 int sde_icdf_poisson(int device, const double* h_u, const double* h_lambda, size_t n, double* h_out);
 /* Merge per-shard (count, mean, M2) triples [n_shards][P][3] -> [P][3] (host, Chan et al.). */
 int sde_moments_merge(const double* shards, size_t n_shards, size_t n_processes, double* out);
+/* The same merge on the device (shards and result in DEVICE memory), asynchronous on `stream` (CUstream, NULL = legacy
+ * default stream): what follows the all-gather of the triples when one process drives one GPU (torch.distributed / MPI). */
+int sde_moments_merge_device(int device, const double* d_shards, size_t n_shards, size_t n_processes, double* d_out, void* stream);
 /* Device microbenchmarks recorded beside MEASURED_PEAKS.json: pure-write GB/s, DFMA / FFMA TFLOP/s. */
 int sde_measure_peaks(int device, double* fill_gbs, double* dfma_tflops, double* ffma_tflops);
 
@@ -202,6 +243,8 @@ const char* sde_last_error(void);
 const char* sde_version(void);
 /* 1 when libcuda + a device are usable from this process. */
 int sde_cuda_available(void);
+/* Number of visible CUDA devices (0 without a driver / GPU). */
+int sde_device_count(void);
 
 #ifdef __cplusplus
 }

@@ -19,12 +19,14 @@ using namespace sde;
 struct sde_universe { Universe u; };
 struct sde_plan { std::unique_ptr<Plan> plan; const double* inject = nullptr; };
 struct sde_result {
-    std::unique_ptr<Plan> plan;
+    std::shared_ptr<Plan> plan;
     DeviceBuffer values;
     uint64_t n = 0;
+    uint64_t scenario_offset = 0;
     size_t elems = 0;
     double kernel_ms = 0.0;
 };
+struct sde_device_plans { std::unique_ptr<DevicePlans> ps; };
 
 namespace {
 thread_local std::string g_error;
@@ -96,6 +98,7 @@ extern "C" {
 
 const char* sde_last_error(void) { return g_error.c_str(); }
 const char* sde_version(void) { return "sde_b200 0.1.0 (sm_100a; reference sde-sim-rs 0.5.1)"; }
+int sde_device_count(void) { try { std::string why; return driver_available(&why) ? device_count() : 0; } catch (...) { return 0; } }
 int sde_cuda_available(void) { std::string why; bool ok = driver_available(&why); if (!ok) g_error = why; return ok ? 1 : 0; }
 
 void sde_options_default(sde_options* o) {
@@ -200,8 +203,9 @@ int sde_simulate(const sde_universe* u, const char* const* init_names, const dou
         sde_options_default(&o);
         if (opt) std::memcpy(&o, opt, std::min<size_t>(sizeof o, opt->struct_size ? opt->struct_size : sizeof o));
         auto r = std::make_unique<sde_result>();
-        r->plan = std::make_unique<Plan>(u->u, po);
+        r->plan = std::make_shared<Plan>(u->u, po);
         r->n = n_scenarios;
+        r->scenario_offset = o.scenario_offset;
         r->elems = r->plan->output_elems(n_scenarios);
         use_device(po.device);
         r->values.alloc(r->plan->output_bytes(n_scenarios));
@@ -233,6 +237,109 @@ int sde_result_values_host(const sde_result* r, double* dst, size_t n_elems) {
     });
 }
 double sde_result_kernel_ms(const sde_result* r) { return r ? r->kernel_ms : 0.0; }
+int sde_result_device(const sde_result* r) { return r ? r->plan->device() : -1; }
+uint64_t sde_result_scenario_offset(const sde_result* r) { return r ? r->scenario_offset : 0; }
+int sde_result_output(const sde_result* r) {
+    if (!r) return -1;
+    const int out = r->plan->options().lower.out;
+    return out == OUT_TERMINAL ? SDE_OUT_TERMINAL : (out == OUT_MOMENTS ? SDE_OUT_MOMENTS : SDE_OUT_PATHS);
+}
+const char* sde_result_process_name(const sde_result* r, size_t i) {
+    return (r && i < r->plan->universe().processes.size()) ? r->plan->universe().processes[i].name.c_str() : nullptr;
+}
+int sde_result_times(const sde_result* r, double* dst, size_t n) {
+    return guarded([&] {
+        if (!r || !dst) throw ExprError{"NULL argument"};
+        const std::vector<double>& t = r->plan->universe().times;
+        if (n < t.size()) throw ExprError{"destination too small"};
+        std::memcpy(dst, t.data(), t.size() * sizeof(double));
+    });
+}
+int sde_result_moments(const sde_result* r, double* dst) {
+    return guarded([&] {
+        if (!r || !dst) throw ExprError{"NULL argument"};
+        if (r->plan->options().lower.out != OUT_MOMENTS) throw ExprError{"sde_result_moments needs output = SDE_OUT_MOMENTS"};
+        use_device(r->plan->device());
+        cu_check(driver().cuMemcpyDtoH(dst, r->values.ptr(), r->plan->universe().processes.size() * 3 * sizeof(double)), "cuMemcpyDtoH");
+    });
+}
+
+// ---- several GPUs, one host thread
+void sde_shard_range(uint64_t n_scenarios, size_t part, size_t n_parts, uint64_t* lo, uint64_t* hi) {
+    if (n_parts == 0 || part >= n_parts) { if (lo) *lo = 0; if (hi) *hi = 0; return; }
+    shard_range(n_scenarios, part, n_parts, lo, hi);
+}
+int sde_device_plans_create(const sde_universe* u, const char* scheme, const char* rng_method, const sde_options* opt,
+                            const int32_t* devices, size_t n_devices, sde_device_plans** out) {
+    return guarded([&] {
+        if (!u || !out) throw ExprError{"NULL argument"};
+        *out = nullptr;
+        if (opt && opt->inject) throw ExprError{"injected draws are a single-device test hook"};
+        PlanOptions po = plan_options(u->u, scheme, rng_method, opt);
+        std::vector<int> devs;
+        if (devices) devs.assign(devices, devices + n_devices);
+        else for (int i = 0; i < device_count(); ++i) devs.push_back(i);          // NULL: every visible device
+        auto h = std::make_unique<sde_device_plans>();
+        h->ps = std::make_unique<DevicePlans>(u->u, po, devs);
+        *out = h.release();
+    });
+}
+void sde_device_plans_free(sde_device_plans* ps) { delete ps; }
+size_t sde_device_plans_count(const sde_device_plans* ps) { return ps ? ps->ps->size() : 0; }
+int sde_device_plans_device(const sde_device_plans* ps, size_t i) { return (ps && i < ps->ps->size()) ? ps->ps->device(i) : -1; }
+int sde_device_plans_collective(const sde_device_plans* ps) { return ps ? ps->ps->collective() : 0; }
+int sde_plan_run_devices(sde_device_plans* ps, const char* const* init_names, const double* init_vals, size_t n_init,
+                         uint64_t n_scenarios, uint64_t seed, uint64_t scenario_offset, double* const* d_out, int* n_launches,
+                         double* collective_ms) {
+    return guarded([&] {
+        if (!ps || !d_out) throw ExprError{"NULL argument"};
+        if (n_scenarios == 0) throw ExprError{"scenarios must be a positive integer"};
+        ps->ps->run(init_pairs(init_names, init_vals, n_init), n_scenarios, seed, scenario_offset, d_out, n_launches, collective_ms);
+    });
+}
+int sde_simulate_devices(const sde_universe* u, const char* const* init_names, const double* init_vals, size_t n_init,
+                         uint64_t n_scenarios, const char* scheme, const char* rng_method, const sde_options* opt,
+                         const int32_t* devices, size_t n_devices, sde_result** out) {
+    return guarded([&] {
+        if (!u || !out) throw ExprError{"NULL argument"};
+        if (n_scenarios == 0) throw ExprError{"scenarios must be a positive integer"};   // py_binding.rs:20-24
+        if (opt && opt->inject) throw ExprError{"injected draws are a single-device test hook"};
+        PlanOptions po = plan_options(u->u, scheme, rng_method, opt);
+        sde_options o;
+        sde_options_default(&o);
+        if (opt) std::memcpy(&o, opt, std::min<size_t>(sizeof o, opt->struct_size ? opt->struct_size : sizeof o));
+        std::vector<int> devs;
+        if (devices) devs.assign(devices, devices + n_devices);
+        else for (int i = 0; i < device_count(); ++i) devs.push_back(i);
+        for (size_t i = 0; i < devs.size(); ++i) out[i] = nullptr;
+        DevicePlans ps(u->u, po, devs);
+        const bool moments = po.lower.out == OUT_MOMENTS;
+        std::vector<std::unique_ptr<sde_result>> rs;
+        std::vector<double*> d_out;
+        for (size_t i = 0; i < ps.size(); ++i) {
+            uint64_t lo, hi;
+            shard_range(n_scenarios, i, ps.size(), &lo, &hi);
+            auto r = std::make_unique<sde_result>();
+            r->plan = ps.plan(i);
+            r->n = moments ? n_scenarios : hi - lo;          // merged moments describe the whole run
+            r->scenario_offset = o.scenario_offset + (moments ? 0 : lo);
+            r->elems = moments ? r->plan->output_elems(1) : (hi > lo ? r->plan->output_elems(hi - lo) : 0);
+            use_device(ps.device(i));
+            if (r->elems) r->values.alloc(moments ? r->elems * 8 : r->plan->output_bytes(hi - lo));
+            d_out.push_back(r->values.as<double>());
+            rs.push_back(std::move(r));
+        }
+        ps.run(init_pairs(init_names, init_vals, n_init), n_scenarios, o.seed, o.scenario_offset, d_out.data(), nullptr, nullptr);
+        for (size_t i = 0; i < rs.size(); ++i) out[i] = rs[i].release();
+    });
+}
+int sde_moments_merge_device(int device, const double* d_shards, size_t n_shards, size_t n_processes, double* d_out, void* stream) {
+    return guarded([&] {
+        if (!d_shards || !d_out) throw ExprError{"NULL argument"};
+        use_device(device);
+        moments_merge_device(device, d_shards, n_shards, n_processes, d_out, (CUstream)stream);
+    });
+}
 
 int sde_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out) {
     return guarded([&] { util_sobol_points(device, dims, first, count, h_out); });

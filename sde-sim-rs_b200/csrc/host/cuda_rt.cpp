@@ -67,6 +67,7 @@ DriverState& driver_state() {
         SDE_LOAD(cuStreamWaitEvent) SDE_LOAD(cuEventCreate) SDE_LOAD(cuEventDestroy) SDE_LOAD(cuEventRecord)
         SDE_LOAD(cuEventSynchronize) SDE_LOAD(cuEventElapsedTime) SDE_LOAD(cuGetErrorString)
         SDE_LOAD(cuOccupancyMaxActiveBlocksPerMultiprocessor)
+        SDE_LOAD(cuMemcpyDtoDAsync) SDE_LOAD(cuMemcpyPeerAsync) SDE_LOAD(cuCtxEnablePeerAccess) SDE_LOAD(cuDeviceCanAccessPeer)
 #undef SDE_LOAD
         if (missing) { st.why = "CUDA driver is missing symbols: " + miss; return; }
         CUresult r = st.api.cuInit(0);
@@ -141,22 +142,52 @@ void cu_check(CUresult r, const char* what) {
     throw CudaError{std::string(what) + ": " + (s ? s : "unknown CUDA error") + " (" + std::to_string((int)r) + ")"};
 }
 
-void use_device(int device) {
+CUcontext device_context(int device) {
     const DriverApi& d = driver();
     static std::mutex mu;
     static CUcontext ctxs[64] = {};
     if (device < 0 || device >= 64) throw CudaError{"bad device ordinal"};
-    CUcontext ctx;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!ctxs[device]) {
-            CUdevice dev;
-            cu_check(d.cuDeviceGet(&dev, device), "cuDeviceGet");
-            cu_check(d.cuDevicePrimaryCtxRetain(&ctxs[device], dev), "cuDevicePrimaryCtxRetain");
-        }
-        ctx = ctxs[device];
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctxs[device]) {
+        CUdevice dev;
+        cu_check(d.cuDeviceGet(&dev, device), "cuDeviceGet");
+        cu_check(d.cuDevicePrimaryCtxRetain(&ctxs[device], dev), "cuDevicePrimaryCtxRetain");
     }
-    cu_check(d.cuCtxSetCurrent(ctx), "cuCtxSetCurrent");
+    return ctxs[device];
+}
+
+void use_device(int device) {
+    cu_check(driver().cuCtxSetCurrent(device_context(device)), "cuCtxSetCurrent");
+}
+
+int device_count() {
+    int n = 0;
+    cu_check(driver().cuDeviceGetCount(&n), "cuDeviceGetCount");
+    return n;
+}
+
+const NcclApi* nccl(std::string* why) {
+    static NcclApi api{};
+    static bool ok = false;
+    static std::string err;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        std::string tried;
+        void* h = open_first(names, &tried);
+        if (!h) { err = "NCCL not found (tried " + tried + ")"; return; }
+        bool missing = false;
+#define SDE_LOAD(field)                                                            \
+        api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, SDE_STR(field))); \
+        if (!api.field) missing = true;
+        SDE_LOAD(ncclCommInitAll) SDE_LOAD(ncclCommDestroy) SDE_LOAD(ncclGroupStart) SDE_LOAD(ncclGroupEnd)
+        SDE_LOAD(ncclAllGather) SDE_LOAD(ncclGetErrorString)
+#undef SDE_LOAD
+        if (missing) { err = "libnccl is missing symbols"; return; }
+        ok = true;
+    });
+    if (!ok && why) *why = err;
+    return ok ? &api : nullptr;
 }
 
 int sm_count(int device) {
@@ -180,10 +211,15 @@ std::mutex g_cache_mu;
 std::unordered_map<uint64_t, std::vector<char>> g_cubin_cache;
 
 std::string cache_dir() {
-    // opt-in: only when the caller names a directory (the Python package points it inside its own build/ tree)
+    // $SDE_B200_CACHE when the caller names a directory (the Python package points it inside its own build/ tree)
     if (std::getenv("SDE_B200_NO_DISK_CACHE")) return "";
-    const char* d = std::getenv("SDE_B200_CACHE");
-    return d ? d : "";
+    if (const char* d = std::getenv("SDE_B200_CACHE")) return d;
+    // default for callers that did not choose a place (the pure-C path): $XDG_CACHE_HOME/sde_b200 or ~/.cache/sde_b200
+    std::string base;
+    if (const char* x = std::getenv("XDG_CACHE_HOME")) base = x;
+    else if (const char* h = std::getenv("HOME")) { base = std::string(h) + "/.cache"; ::mkdir(base.c_str(), 0755); }
+    if (base.empty()) return "";
+    return base + "/sde_b200";
 }
 bool read_file(const std::string& path, std::vector<char>* out) {
     FILE* f = std::fopen(path.c_str(), "rb");

@@ -51,7 +51,24 @@ struct DriverApi {
     CUresult (*cuEventElapsedTime)(float*, CUevent, CUevent);
     CUresult (*cuGetErrorString)(CUresult, const char**);
     CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+    CUresult (*cuMemcpyDtoDAsync)(CUdeviceptr, CUdeviceptr, size_t, CUstream);
+    CUresult (*cuMemcpyPeerAsync)(CUdeviceptr, CUcontext, CUdeviceptr, CUcontext, size_t, CUstream);
+    CUresult (*cuCtxEnablePeerAccess)(CUcontext, unsigned);
+    CUresult (*cuDeviceCanAccessPeer)(int*, CUdevice, CUdevice);
 };
+
+// NCCL, dlopen'ed like the driver (libnccl.so.2: the copy PyTorch already mapped when running under it, else the
+// system's).  Only what the moment all-gather needs (3 P doubles per rank).
+struct NcclApi {
+    int (*ncclCommInitAll)(void** comms, int ndev, const int* devlist);
+    int (*ncclCommDestroy)(void* comm);
+    int (*ncclGroupStart)();
+    int (*ncclGroupEnd)();
+    int (*ncclAllGather)(const void* send, void* recv, size_t count, int dtype, void* comm, CUstream stream);
+    const char* (*ncclGetErrorString)(int);
+};
+// nullptr when libnccl cannot be loaded (the callers then fall back to peer-to-peer copies)
+const NcclApi* nccl(std::string* why = nullptr);
 
 struct NvrtcApi {
     nvrtcResult (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
@@ -75,7 +92,9 @@ void cu_check(CUresult r, const char* what);
 // Makes the primary context of `device` current on this thread (shared with the CUDA
 // runtime / PyTorch, so their device pointers are valid here).
 void use_device(int device);
+CUcontext device_context(int device);
 int sm_count(int device);
+int device_count();
 
 struct EmbeddedHeader { const char* name; const char* begin; const char* end; };
 // Compile `source` for sm_100a with the embedded kernel headers; returns the cubin.

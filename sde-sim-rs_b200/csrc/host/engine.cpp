@@ -284,6 +284,8 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
         const uint64_t items = 4 * ((first_n + n - base128 + 127) / 128);
         const uint64_t warps = block / 32;
         grid = std::min<uint64_t>((items + warps - 1) / warps, (uint64_t)sm_count(opt_.device) * (uint64_t)low_.min_blocks);
+        // a CTA serves one item class (item mod 4 = blockIdx mod 4: one step shift per CTA): whole groups of 4 CTAs
+        grid = std::max<uint64_t>(4, grid & ~3ull);
     }
     if (grid == 0 || n == 0) return;
     if (low_.resident) {
@@ -393,7 +395,8 @@ void Plan::run_host(const std::vector<std::pair<std::string, double>>& init, uin
 namespace {
 struct UtilModule {
     CUmodule mod = nullptr;
-    CUfunction sobol = nullptr, chacha = nullptr, icdf = nullptr, icdf_wide = nullptr, poisson = nullptr, fill = nullptr, dfma = nullptr, ffma = nullptr;
+    CUfunction sobol = nullptr, chacha = nullptr, icdf = nullptr, icdf_wide = nullptr, poisson = nullptr, fill = nullptr, dfma = nullptr, ffma = nullptr,
+               merge = nullptr;
 };
 UtilModule& util_module(int device) {
     static std::mutex mu;
@@ -413,6 +416,7 @@ UtilModule& util_module(int device) {
         cu_check(d.cuModuleGetFunction(&m.fill, m.mod, "sde_k_fill"), "sde_k_fill");
         cu_check(d.cuModuleGetFunction(&m.dfma, m.mod, "sde_k_dfma"), "sde_k_dfma");
         cu_check(d.cuModuleGetFunction(&m.ffma, m.mod, "sde_k_ffma"), "sde_k_ffma");
+        cu_check(d.cuModuleGetFunction(&m.merge, m.mod, "sde_k_moments_merge"), "sde_k_moments_merge");
     }
     return m;
 }
@@ -457,8 +461,9 @@ void util_icdf_normal(int device, int mode, const double* h_p, size_t n, double*
     din.upload(h_p, n * 8);
     uint64_t nn = n;
     CUdeviceptr pi = din.ptr(), po = dout.ptr();
-    if (mode == 5) {                                         // 32-bit front end, 1024-entry log table
-        void* wargs[] = {&pi, &nn, &po};
+    if (mode == 5 || mode == 6) {                            // 32-bit front end, 1024-entry log table (6: FP32-unit seeds)
+        int f32seed = mode == 6 ? 1 : 0;
+        void* wargs[] = {&pi, &nn, &po, &f32seed};
         launch1d(m.icdf_wide, std::min<uint64_t>((n + 255) / 256, 1184), 256, 1024 * 2 * 8 * 8, wargs);
     } else {
         void* args[] = {&pi, &nn, &mode, &po};
@@ -529,6 +534,150 @@ void util_measure_peaks(int device, double* fill_gbs, double* dfma_tflops, doubl
     }
     d.cuEventDestroy(e0);
     d.cuEventDestroy(e1);
+}
+
+void moments_merge_device(int device, const double* d_shards, size_t n_shards, size_t P, double* d_out, CUstream stream) {
+    UtilModule& m = util_module(device);
+    CUdeviceptr ps = (CUdeviceptr)d_shards, po = (CUdeviceptr)d_out;
+    uint64_t ns = n_shards;
+    int p = (int)P;
+    void* args[] = {&ps, &ns, &p, &po};
+    cu_check(driver().cuLaunchKernel(m.merge, (unsigned)((P + 127) / 128), 1, 1, 128, 1, 1, 0, stream, args, nullptr), "cuLaunchKernel(sde_k_moments_merge)");
+}
+
+void shard_range(uint64_t n, size_t part, size_t parts, uint64_t* lo, uint64_t* hi) {
+    const uint64_t base = n / parts, rem = n % parts, i = part;
+    const uint64_t l = i * base + std::min<uint64_t>(i, rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (i < rem ? 1 : 0);
+}
+
+DevicePlans::DevicePlans(const Universe& u, const PlanOptions& opt, const std::vector<int>& devices) : devices_(devices) {
+    if (devices_.empty()) throw ExprError{"device list is empty"};
+    const int n_dev = device_count();
+    bool repeated = false;                                   // a device listed twice (several shards on one GPU): fine, but not for NCCL
+    for (size_t i = 0; i < devices_.size(); ++i) {
+        if (devices_[i] < 0 || devices_[i] >= n_dev) throw ExprError{"device ordinal " + std::to_string(devices_[i]) + " out of range (" + std::to_string(n_dev) + " visible)"};
+        for (size_t j = 0; j < i; ++j) if (devices_[j] == devices_[i]) repeated = true;
+    }
+    for (int dev : devices_) {
+        PlanOptions po = opt;
+        po.device = dev;
+        plans_.push_back(std::make_shared<Plan>(u, po));    // same lowering: the cubin comes out of the in-memory cache after the first
+    }
+    const size_t G = devices_.size(), P = (size_t)u.P();
+    if (opt.lower.out == OUT_MOMENTS && G > 1) {
+        const DriverApi& d = driver();
+        local_.resize(G);
+        gathered_.resize(G);
+        ev_local_.assign(G, nullptr);
+        for (size_t i = 0; i < G; ++i) {
+            use_device(devices_[i]);
+            local_[i].alloc(P * 3 * 8);
+            gathered_[i].alloc(G * P * 3 * 8);
+            cu_check(d.cuEventCreate(&ev_local_[i], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+        }
+        use_device(devices_[0]);
+        cu_check(d.cuEventCreate(&ev_c0_, CU_EVENT_DEFAULT), "cuEventCreate");
+        cu_check(d.cuEventCreate(&ev_c1_, CU_EVENT_DEFAULT), "cuEventCreate");
+        collective_ = 2;
+        if (!repeated && !std::getenv("SDE_B200_NO_NCCL")) {
+            if (const NcclApi* nc = nccl()) {
+                comms_.assign(G, nullptr);
+                const int rc = nc->ncclCommInitAll(comms_.data(), (int)G, devices_.data());
+                if (rc == 0) collective_ = 1;
+                else comms_.clear();                         // e.g. a NCCL build without these GPUs: peer copies still work
+            }
+        }
+        if (collective_ == 2) {
+            for (size_t i = 0; i < G; ++i)
+                for (size_t j = 0; j < G; ++j) {
+                    if (devices_[i] == devices_[j]) continue;
+                    use_device(devices_[i]);
+                    const CUresult r = d.cuCtxEnablePeerAccess(device_context(devices_[j]), 0);
+                    (void)r;                                 // already enabled / not supported: cuMemcpyPeerAsync stages through the host then
+                }
+        }
+    }
+}
+
+DevicePlans::~DevicePlans() {
+    std::string why;
+    if (!driver_available(&why)) return;
+    const DriverApi& d = driver();
+    try {
+        for (size_t i = 0; i < plans_.size(); ++i) {
+            use_device(devices_[i]);
+            d.cuStreamSynchronize(plans_[i]->stream());
+            if (i < ev_local_.size() && ev_local_[i]) d.cuEventDestroy(ev_local_[i]);
+            if (i < local_.size()) { local_[i].release(); gathered_[i].release(); }
+        }
+        if (ev_c0_) { use_device(devices_[0]); d.cuEventDestroy(ev_c0_); d.cuEventDestroy(ev_c1_); }
+        if (!comms_.empty()) if (const NcclApi* nc = nccl()) for (void* c : comms_) if (c) nc->ncclCommDestroy(c);
+    } catch (...) {}
+}
+
+void DevicePlans::run(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed, uint64_t scenario_offset,
+                      double* const* d_out, int* n_launches, double* collective_ms) {
+    const DriverApi& d = driver();
+    const size_t G = plans_.size(), P = (size_t)plans_[0]->universe().P();
+    const bool moments = plans_[0]->options().lower.out == OUT_MOMENTS;
+    if (!d_out) throw ExprError{"d_out must not be NULL"};
+    if (collective_ms) *collective_ms = 0.0;
+    // 1. every device's shard is launched on its plan's stream; nothing is synchronised in this loop once the plans
+    //    hold their tables (first call: initial row / digital-shift masks are uploaded)
+    for (size_t i = 0; i < G; ++i) {
+        uint64_t lo, hi;
+        shard_range(n, i, G, &lo, &hi);
+        use_device(devices_[i]);
+        double* dst = (moments && G > 1) ? local_[i].as<double>() : d_out[i];
+        if (hi > lo) {
+            if (!dst) throw ExprError{"d_out[" + std::to_string(i) + "] must not be NULL"};
+            plans_[i]->run_device(init, hi - lo, seed, scenario_offset + lo, dst, nullptr, plans_[i]->stream(), n_launches);
+        } else if (moments && G > 1) {
+            cu_check(d.cuMemsetD8Async(local_[i].ptr(), 0, P * 3 * 8, plans_[i]->stream()), "cuMemsetD8Async");   // count 0: skipped by the merge
+        }
+        if (moments && G > 1 && collective_ == 2) cu_check(d.cuEventRecord(ev_local_[i], plans_[i]->stream()), "cuEventRecord");
+    }
+    // 2. moments: all-gather of the 3 P doubles per device + merge kernel, on the compute streams
+    if (moments && G > 1) {
+        use_device(devices_[0]);
+        cu_check(d.cuEventRecord(ev_c0_, plans_[0]->stream()), "cuEventRecord");
+        if (collective_ == 1) {
+            const NcclApi* nc = nccl();
+            auto nccl_check = [&](int rc, const char* what) { if (rc != 0) throw CudaError{std::string(what) + ": " + nc->ncclGetErrorString(rc)}; };
+            nccl_check(nc->ncclGroupStart(), "ncclGroupStart");
+            for (size_t i = 0; i < G; ++i)
+                nccl_check(nc->ncclAllGather(local_[i].as<double>(), gathered_[i].as<double>(), P * 3, /*ncclDouble*/ 8, comms_[i], plans_[i]->stream()), "ncclAllGather");
+            nccl_check(nc->ncclGroupEnd(), "ncclGroupEnd");
+        } else {
+            for (size_t j = 0; j < G; ++j) {                 // destination device j pulls every shard's triple
+                use_device(devices_[j]);
+                for (size_t i = 0; i < G; ++i) {
+                    if (i != j) cu_check(d.cuStreamWaitEvent(plans_[j]->stream(), ev_local_[i], 0), "cuStreamWaitEvent");
+                    cu_check(d.cuMemcpyPeerAsync(gathered_[j].ptr() + i * P * 3 * 8, device_context(devices_[j]), local_[i].ptr(),
+                                                 device_context(devices_[i]), P * 3 * 8, plans_[j]->stream()), "cuMemcpyPeerAsync");
+                }
+            }
+        }
+        for (size_t i = 0; i < G; ++i) {
+            use_device(devices_[i]);
+            if (d_out[i]) moments_merge_device(devices_[i], gathered_[i].as<double>(), G, P, d_out[i], plans_[i]->stream());
+            if (n_launches && d_out[i]) ++*n_launches;
+        }
+        use_device(devices_[0]);
+        cu_check(d.cuEventRecord(ev_c1_, plans_[0]->stream()), "cuEventRecord");
+    }
+    // 3. wait for everything
+    for (size_t i = 0; i < G; ++i) {
+        use_device(devices_[i]);
+        cu_check(d.cuStreamSynchronize(plans_[i]->stream()), "cuStreamSynchronize");
+    }
+    if (moments && G > 1 && collective_ms) {
+        float ms = 0;
+        d.cuEventElapsedTime(&ms, ev_c0_, ev_c1_);
+        *collective_ms = ms;
+    }
 }
 
 void moments_merge(const double* shards, size_t n_shards, size_t P, double* out) {

@@ -53,6 +53,7 @@ class Plan {
                   uint64_t scenario_offset, double* h_out, int* n_launches);
     double last_kernel_ms() const { return last_ms_; }
     int device() const { return opt_.device; }
+    CUstream stream() const { return own_stream_; }          // the plan's own (non-blocking) stream
 
   private:
     Universe u_;
@@ -75,6 +76,40 @@ class Plan {
     void ensure_masks(uint64_t seed, CUstream stream);
     void launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d_out, const double* d_inject, CUstream stream, int* n_launches);
 };
+
+// ---- several GPUs of one box driven by ONE host thread: replaces the rayon par_iter over scenarios inside
+// sim::simulate (src/sim/mod.rs:41-43).  Device i of G simulates scenarios shard_range(N, i, G) (disjoint Sobol index
+// ranges / ChaCha keys: the union is bit-identical to a one-device run).  Every launch is issued before any device is
+// synchronised.  Moments: each device reduces its shard, the 3 P doubles per device are all-gathered over NCCL
+// (ncclAllGather inside one group, on the compute streams) and Chan-merged by a device kernel right behind it, so every
+// device ends up with the merged [P][3]; without libnccl the same gather runs as peer-to-peer copies.
+void shard_range(uint64_t n, size_t part, size_t parts, uint64_t* lo, uint64_t* hi);
+class DevicePlans {
+  public:
+    DevicePlans(const Universe& u, const PlanOptions& opt, const std::vector<int>& devices);
+    ~DevicePlans();
+    DevicePlans(const DevicePlans&) = delete;
+    DevicePlans& operator=(const DevicePlans&) = delete;
+    size_t size() const { return plans_.size(); }
+    const std::shared_ptr<Plan>& plan(size_t i) const { return plans_[i]; }
+    int device(size_t i) const { return devices_[i]; }
+    int collective() const { return collective_; }           // 0 none, 1 NCCL, 2 peer-to-peer copies
+    // d_out[i]: device memory on device i for that shard's rows / terminal values ([n_i][T][P] / [n_i][P]) or, for moments,
+    // the merged [P][3] (every device receives it).  Synchronous: returns when every device has finished.
+    void run(const std::vector<std::pair<std::string, double>>& init, uint64_t n, uint64_t seed, uint64_t scenario_offset,
+             double* const* d_out, int* n_launches, double* collective_ms);
+
+  private:
+    std::vector<std::shared_ptr<Plan>> plans_;
+    std::vector<int> devices_;
+    int collective_ = 0;
+    std::vector<void*> comms_;                                // ncclComm_t per device
+    std::vector<DeviceBuffer> local_, gathered_;              // [P][3] / [G][P][3] per device
+    std::vector<CUevent> ev_local_;                           // shard moments ready (peer-copy path)
+    CUevent ev_c0_ = nullptr, ev_c1_ = nullptr;               // collective + merge on device 0
+};
+// Chan merge of [n_shards][P][3] on the device (util cubin), asynchronous on `stream` of `device`
+void moments_merge_device(int device, const double* d_shards, size_t n_shards, size_t P, double* d_out, CUstream stream);
 
 // ---- stand-alone building blocks (ahead-of-time cubin)
 void util_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out);

@@ -373,7 +373,11 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         const bool same = lo == hi;
         const bool close = !opt.strict && std::isfinite(lo) && std::isfinite(hi) && (hi - lo) <= std::ldexp(std::fabs(med), -44);
         if (same || close) {
-            slot_macro[i] = "(" + format_real(med) + ")";
+            // f64 plans: as a uniform-datapath value (sde_uc, sde_expr_helpers.cuh) so that fma(SLOT, z, g) reads two
+            // register pairs, not three
+            // register pairs, not three.  Slot 0 of a process is the addend the factor terms accumulate onto: a plain literal.
+            const bool multiplier = gen.slots[i].find("sqrt_dt") != std::string::npos;
+            slot_macro[i] = (opt.f32 || !multiplier) ? "(" + format_real(med) + ")" : "sde_uc(" + format_real(med) + ")";
         } else {
             slot_macro[i] = "((sde_real)ss[" + std::to_string(4 + table_slots.size()) + "])";
             table_slots.push_back(gen.slots[i]);
@@ -401,14 +405,15 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         auto resident_smem = [&](int block, int nslot_) {     // mirrors the SDE_SMEM_* macros of sde_sim_resident.cuh
             const size_t sk = (size_t)S * K;
             size_t icdf = (opt.icdf == 1) ? (wide ? (size_t)1024 * 2 * 8 * 8 : (size_t)(128 * 2 * 8 + 64) * 8) : 0;
-            return icdf + (size_t)S * (4 + nslot_) * 8 + sk * 128 + (size_t)(block / 32) * ((sk + 3) & ~(size_t)3) * 4;
+            const size_t nq = (sk + 3 + 3) / 4;               // SDE_NQ: quads of 4 dimensions (+ room for the per-CTA offset)
+            return icdf + (size_t)S * (4 + nslot_) * 8 + nq * 512 + (size_t)(block / 32) * nq * 16;
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
         if (eligible && opt.direct != 1) {
-            // 16 warps per SM (4 per scheduler), measured on B200 (profiles/r1_sweep_resident.json): the software-pipelined
-            // step loop carries its own instruction-level parallelism, and under sustained load the kernel is held by the
-            // board power limit (sw_power_cap, ~1.70-1.75 GHz), where 12-32 warps all land within 2 %
-            int block = opt.block > 0 ? opt.block : 512;
+            // 24 warps per SM (6 per scheduler), measured on B200 (profiles/r2_c2_ab.md): the step loop needs 64-80 registers,
+            // and since its FP64 instructions stopped paying for three register-pair operands (sde_uc, FP32-unit seeds)
+            // more resident warps pay again: 485 G path-steps/s sustained at 768 threads, 478 at 512, 480 at 1024
+            int block = opt.block > 0 ? opt.block : 768;
             block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
             while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
             if (resident_smem(block, nslot) <= 200 * 1024) {
@@ -542,15 +547,12 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";
         if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
+        if (K > 0 && std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; })) s << "#define SDE_ALL_WIENER 1\n";
         if (std::getenv("SDE_B200_DEBUG_NOCOMPUTE")) s << "#define SDE_DEBUG_NOCOMPUTE 1\n";                                              // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSCALAR")) s << "#define SDE_DEBUG_NOSCALAR 1\n";                                                // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSTORE")) s << "#define SDE_DEBUG_NOSTORE 1\n";                                                  // profiling aid
         if (const char* g = std::getenv("SDE_B200_RES_PIPE")) s << "#define SDE_RES_PIPE " << (std::atoi(g) ? 1 : 0) << "\n";          // tuning
-        // steps per unrolled group: 4 (one sector store per lane per process); 8 measured equal within noise on C2
-        // (SDE_B200_RES_GRP overrides for tuning)
-        int grp = 4;
-        if (const char* g = std::getenv("SDE_B200_RES_GRP")) grp = std::atoi(g) == 8 ? 8 : 4;
-        s << "#define SDE_RES_GRP " << grp << "\n";
+        s << "#define SDE_RES_GRP 4\n";                      // steps per unrolled group: one sector store per lane and process
     }
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";

@@ -81,7 +81,13 @@ __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, in
 
 // Constants of the FAST path live in constant memory so that FP64 instructions read them as
 // c[bank][offset] operands instead of spending issue slots on 64-bit immediate moves.
-__constant__ double sde_kc[12] = {
+#ifndef SDE_ICDF_HORNER
+#define SDE_ICDF_HORNER 1                       /* FP32-seed variant: N(t), D(t) by Horner in t (0: the even/odd split in w = t^2) */
+#endif
+#ifndef SDE_ICDF_F32SEED
+#define SDE_ICDF_F32SEED 1                      /* wide-table map: 1 = FP32-unit seeds + quadratic steps (see below), 0 = MUFU.*64H seeds + cubic steps */
+#endif
+__constant__ double sde_kc[24] = {
     0x1.0000999a03338p-1,   // 0  a3  } degree-3 minimax polynomial for -2 log1p(r) / r on |r| <= 2^-8,
     -0x1.55560888fbbc1p-1,  // 1  a2  } a1 = 1, a0 = -2 exact  (max |err| 4.9e-14 absolute in -2 ln w)
     SDE_AS_C2, SDE_AS_C1, SDE_AS_C0,       // 2..4
@@ -89,10 +95,28 @@ __constant__ double sde_kc[12] = {
     0.375,                                 // 8   3/8 of the cubic square-root step
     -2.772588722239781,                    // 9   -4 ln 2: exponent term, D = 32 + pos/2 variant
     -1.3862943611198906,                   // 10  -2 ln 2: exponent term, converted-integer variant
-    -0.6666666666666666};
-// SDE_KC(i): coefficient i of the FAST path.  Default: the __constant__ array above.  SDE_KC_LITERAL (tuning only): the same values
-// as literals, which ptxas places on uniform-register operands more often (operand forms).
+    -0.6666666666666666,     // 12..: the FP32-seed variant works on 16 x (-2 ln w) (see sde_icdf_as_tail_f32seed): the same coefficients times powers of two
+    -0.25 + 9.5e-15,                       // 12  -1/4 (+ half of the largest second-order term left out by the quadratic square-root step)
+    -1.3862943611198906 * 16.0,            // 13  16 x (-2 ln 2)
+    -0.6666666666666666 * 16.0,            // 14  16 x (-2/3)
+    SDE_AS_C0 * 16.0, SDE_AS_C1 * 16.0,    // 15, 16
+    SDE_AS_D1 * 16.0,                      // 17
+    SDE_AS_C2 * 16.0, SDE_AS_D3 * 16.0, SDE_AS_D2 * 16.0};   // 18, 19, 20
+// SDE_KC(i): coefficient i of the FAST path.
+//   SDE_KC_MODE 0  the __constant__ array above (ptxas hoists the loads into vector registers)
+//   SDE_KC_MODE 1  literals (same)
+//   SDE_KC_MODE 2  uniform-datapath values, sde_uc() in sde_expr_helpers.cuh: uniform-register DFMA operands (default
+//                  where that header is included, i.e. in the fused kernels)
+#ifndef SDE_KC_MODE
 #ifdef SDE_KC_LITERAL
+#define SDE_KC_MODE 1
+#elif defined(SDE_UC)
+#define SDE_KC_MODE (SDE_UC ? 2 : 0)
+#else
+#define SDE_KC_MODE 0
+#endif
+#endif
+#if SDE_KC_MODE
 #define SDE_KCL_0 (0x1.0000999a03338p-1)
 #define SDE_KCL_1 (-0x1.55560888fbbc1p-1)
 #define SDE_KCL_2 (SDE_AS_C2)
@@ -105,11 +129,28 @@ __constant__ double sde_kc[12] = {
 #define SDE_KCL_9 (-2.772588722239781)
 #define SDE_KCL_10 (-1.3862943611198906)
 #define SDE_KCL_11 (-0.6666666666666666)
+#define SDE_KCL_12 (-0.25 + 9.5e-15)
+#define SDE_KCL_13 (-1.3862943611198906 * 16.0)
+#define SDE_KCL_14 (-0.6666666666666666 * 16.0)
+#define SDE_KCL_15 (SDE_AS_C0 * 16.0)
+#define SDE_KCL_16 (SDE_AS_C1 * 16.0)
+#define SDE_KCL_17 (SDE_AS_D1 * 16.0)
+#define SDE_KCL_18 (SDE_AS_C2 * 16.0)
+#define SDE_KCL_19 (SDE_AS_D3 * 16.0)
+#define SDE_KCL_20 (SDE_AS_D2 * 16.0)
 #define SDE_KC(i) SDE_KCL_##i
+#if SDE_KC_MODE == 2
+// SDE_KU(i): a coefficient that is the ONLY non-register operand of its instruction (a DFMA takes one uniform-register,
+// constant or immediate operand): those go through the uniform datapath; coefficients that share their instruction
+// with an immediate or with another coefficient stay SDE_KC (a vector register)
+#define SDE_KU(i) sde_uc(SDE_KCL_##i)
+#else
+#define SDE_KU(i) SDE_KCL_##i
+#endif
 #else
 #define SDE_KC(i) sde_kc[i]
+#define SDE_KU(i) sde_kc[i]
 #endif
-                  // 11  -2/3: cubic Taylor term of the wide-table logarithm
 
 // Core: w = 1.mb * 2^e in (0, 0.5], given as mantissa bits (52 bits in hi:lo, leading one removed) and the
 // byte offset `eoff` of the exponent term in the eln2 table.  Returns A&S x(w) (caller applies the sign).
@@ -126,7 +167,15 @@ __constant__ double sde_kc[12] = {
 #ifndef SDE_SEED_GARBAGE_LOW
 #define SDE_SEED_GARBAGE_LOW 1
 #endif
-#if SDE_SEED_GARBAGE_LOW
+#if SDE_SEED_GARBAGE_LOW == 2
+// the low word is a register that is never written: ptxas is free to pair the seed's high word with any dead register
+__device__ __forceinline__ double sde_seed_junk_low(double seed) {
+    double r;
+    asm("{ .reg .b32 lo, hi, junk; mov.b64 {lo, hi}, %1; mov.b64 %0, {junk, hi}; }" : "=d"(r) : "d"(seed));
+    return r;
+}
+#define SDE_SEED_LOW(seed, donor) sde_seed_junk_low(seed)
+#elif SDE_SEED_GARBAGE_LOW
 #define SDE_SEED_LOW(seed, donor) __hiloint2double(__double2hiint(seed), __double2loint(donor))
 #else
 #define SDE_SEED_LOW(seed, donor) (seed)
@@ -147,16 +196,23 @@ __device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double
     const double g = w2 * y0;
     const double e2 = fma(-g, y0, 1.0);
     const double ps = fma(e2, SDE_KC(8), 0.5);
+#ifdef SDE_SEED_DONOR_LOCAL
+    const double ep = e2 * ps;
+    const double t = fma(g, ep, g);
+#define SDE_R0_DONOR ep
+#else
     const double t = fma(g, e2 * ps, g);
+#define SDE_R0_DONOR d2
+#endif
     // N(t) = (c0 + c2 w2) + c1 t and D(t) = (1 + d2 w2) + t (d1 + d3 w2): t^2 = w2 is known before the square root
     // is, so only one FMA of each polynomial waits for t (same operation count as Horner, shorter critical path)
-    const double ne = fma(SDE_KC(2), w2, SDE_KC(4));
+    const double ne = fma(SDE_KU(2), w2, SDE_KC(4));
     const double de = fma(SDE_KC(6), w2, 1.0);
-    const double dd = fma(SDE_KC(5), w2, SDE_KC(7));
-    const double num = fma(SDE_KC(3), t, ne);
+    const double dd = fma(SDE_KU(5), w2, SDE_KC(7));
+    const double num = fma(SDE_KU(3), t, ne);
     const double den = fma(t, dd, de);
     // x = t - N/D with 1/D = r0 (1 + ed + ed^2), ed = 1 - D r0 (cubic step on the MUFU seed), folded into one final FMA
-    const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), d2);
+    const double r0 = SDE_SEED_LOW(sde_rcp_approx(den), SDE_R0_DONOR);
     const double ed = fma(-den, r0, 1.0);
     const double r1 = fma(r0, fma(ed, ed, ed), r0);
     return fma(-num, r1, t);
@@ -237,10 +293,7 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32(sde_u32 k, const doub
 // replica of log-table entry 0 of a table loaded with y_offset = SDE_ICDF_Y_OFFSET_K32.  Two integer instructions
 // per table address, and the compiler cannot rematerialise the lane-dependent part inside the step loop.
 // One shared-memory access per draw (LDS.128): the load/store data pipe is this kernel's busiest unit.
-__device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 tab_lane) {
-    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
-    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
-    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+__device__ __forceinline__ double sde_icdf_fast_j32s(sde_u32 j, sde_u32 neg, sde_u32 tab_lane) {
     int pos;
     asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(j));
     const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned
@@ -257,12 +310,23 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 t
     asm("mad.lo.u32 %0, %1, 16384, 0x40400000;" : "=r"(dh) : "r"((sde_u32)pos));
     const double base = fma(__hiloint2double((int)dh, 0), SDE_KC(9), tc.y);
 #else
-    const double base = fma((double)pos, SDE_KC(10), tc.y);
+    const double base = fma((double)pos, SDE_KU(10), tc.y);
 #endif
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double x = sde_icdf_as_core_b(m, tc, base);
-    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
+    const int xhi = __double2hiint(x) ^ (int)(neg & 0x80000000u);
     return __hiloint2double(xhi, __double2loint(x));
+}
+__device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 tab_lane) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+    return sde_icdf_fast_j32s(j, ~(sde_u32)sgn, tab_lane);   // p < 0.5 -> -x
+}
+__device__ __forceinline__ double sde_icdf_normal_fast_y32s(sde_u32 y, sde_u32 tab_lane) {   // sign-folded entry, see y32w
+    sde_u32 j;
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(y));
+    return sde_icdf_fast_j32s(j, ~y, tab_lane);
 }
 
 // ---- wide log table (persistent kernel, when shared memory allows): 1024 entries x 8 replicas = 128 KB.
@@ -271,19 +335,59 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32s(sde_u32 k, sde_u32 t
 // -2 ln c = 2 ln(invc) for exactly that invc (CUDA's f64 log: <= 1 ulp), so no constant array is needed.
 #define SDE_ICDF_WIDE_BITS 10
 #define SDE_ICDF_WIDE_DOUBLES ((1 << SDE_ICDF_WIDE_BITS) * 2 * SDE_ICDF_TABLE_REPL)
-__device__ __forceinline__ void sde_icdf_wide_table_build(double* s_table, int tid, int nthreads, double y_offset) {
+__device__ __forceinline__ void sde_icdf_wide_table_build(double* s_table, int tid, int nthreads, double y_offset,
+                                                          double y_scale = (SDE_ICDF_F32SEED ? 16.0 : 1.0)) {
     for (int i = tid; i < (1 << SDE_ICDF_WIDE_BITS) * SDE_ICDF_TABLE_REPL; i += nthreads) {
         const int idx = i / SDE_ICDF_TABLE_REPL;
         const double c_mid = 1.0 + ((double)idx + 0.5) * (1.0 / (double)(1 << SDE_ICDF_WIDE_BITS));
         const double invc = __ddiv_rn(1.0, c_mid);
         s_table[2 * i] = invc;
-        s_table[2 * i + 1] = __dadd_rn(__dmul_rn(2.0, log(invc)), y_offset);
+        s_table[2 * i + 1] = __dadd_rn(__dmul_rn(2.0, log(invc)), y_offset) * y_scale;   // 1 or 16: exact scaling
     }
 }
-__device__ __forceinline__ double sde_icdf_normal_fast_k32w(sde_u32 k, sde_u32 tab_lane) {
-    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
-    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
-    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+// FP32-unit seeds (SDE_ICDF_F32SEED): everything after the logarithm with MUFU.RSQ / MUFU.RCP (FP32: relative error 2^-22.4
+// on the operand truncated to 24 bits, measured in tools/ubench/mufu_seed.cu; MUFU.RSQ64H / RCP64H only reach 2^-20) and
+// ONE quadratic step each — 6 FP64 instructions for sqrt and 1/D instead of 9.  The operands travel between the f64 and
+// f32 formats as bit patterns (funnel shift in, shift + add out), which only works when their exponents sit where the
+// low 8 bits of the f64 exponent field are a valid f32 exponent: the map is therefore evaluated on w16 = 16 x (-2 ln w)
+// and 16 D(t) (all coefficients scaled by powers of two: bit-identical products), whose f64 exponent fields 0x403..0x409
+// read as f32 values 2^-128 times smaller.
+//   sqrt:  s = (1/2) w16^-1/2 (1 + e),  P = w16 s,  E = -P s - 1/4 = -1/2 + e2/4  (e2 = 1 - (1+e)^2),
+//          t = P + P E = (1/4) w16^1/2 (1 - 3/8 e2^2 ...) = sqrt(-2 ln w): relative error <= 3.8e-14, centred by the constant
+//   1/D:   r0 = 1/(16 D) (1 + e),  ed = 1 - 16 D r0,  r1 = r0 + r0 ed   (relative error ed^2 <= 3e-14)
+// Stated tolerance of the map unchanged: |dz| <= 5e-13 absolute vs the REFERENCE evaluation (tests/test_gpu_blocks.py).
+__device__ __forceinline__ double sde_icdf_as_tail_f32seed(const double w16) {
+    float ys, rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ys) : "f"(__uint_as_float(__funnelshift_l((sde_u32)__double2loint(w16), (sde_u32)__double2hiint(w16), 3))));
+    const sde_u32 yb = __float_as_uint(ys);                  // ys = w16^-1/2 2^64
+    const double s = __hiloint2double((int)((yb >> 3) + 0x33F00000u), (int)(yb << 29));   // ys 2^-65
+    const double P = w16 * s;
+    const double E = fma(-P, s, SDE_KU(12));
+    const double t = fma(P, E, P);
+#if SDE_ICDF_HORNER
+    // 16 N(t) and 16 D(t) by Horner in t: every instruction reads two register pairs (t and the running value) plus a
+    // uniform-register or immediate coefficient — no three-pair DFMA (the even/odd split below ends in den = t dd + de)
+    const double num = fma(fma(t, SDE_KU(18), SDE_KC(16)), t, SDE_KU(15));
+    const double den = fma(fma(fma(t, SDE_KU(19), SDE_KC(20)), t, SDE_KU(17)), t, 16.0);
+#else
+    // 16 N(t) = (16 c0 + c2 w16) + 16 c1 t,  16 D(t) = (16 + d2 w16) + t (16 d1 + d3 w16)
+    const double ne = fma(SDE_KU(2), w16, SDE_KC(15));
+    const double de = fma(SDE_KC(6), w16, 16.0);
+    const double dd = fma(SDE_KU(5), w16, SDE_KC(17));
+    const double num = fma(SDE_KU(16), t, ne);
+    const double den = fma(t, dd, de);
+#endif
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(__uint_as_float(__funnelshift_l((sde_u32)__double2loint(den), (sde_u32)__double2hiint(den), 3))));
+    const sde_u32 rb = __float_as_uint(rs);                  // rs = 2^128 / (16 D)
+    const double r0 = __hiloint2double((int)((rb >> 3) + 0x30000000u), (int)(rb << 29));   // rs 2^-128
+    const double ed = fma(-den, r0, 1.0);
+    const double r1 = fma(r0, ed, r0);
+    return fma(-num, r1, t);
+}
+// core of the wide-table map: j = 2 v + 1 with v = the 31 folded bits of min(p, 1-p) 2^32 - 1/2; `neg` has bit 31 set when
+// the result is to be negated (p < 1/2)
+template <int F32SEED>
+__device__ __forceinline__ double sde_icdf_fast_j32w_t(sde_u32 j, sde_u32 neg, sde_u32 tab_lane) {
     int pos;
     asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(j));
     const sde_u32 mh = __funnelshift_r(0u, j, pos);          // bits below the leading one, left aligned
@@ -291,14 +395,38 @@ __device__ __forceinline__ double sde_icdf_normal_fast_k32w(sde_u32 k, sde_u32 t
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ta) : "r"(mh >> (32 - SDE_ICDF_WIDE_BITS)), "r"(16u * SDE_ICDF_TABLE_REPL), "r"(tab_lane));
     double2 tc;                                              // {1/c, -2 ln c + 66 ln 2}
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tc.x), "=d"(tc.y) : "r"(ta));
-    const double base = fma((double)pos, SDE_KC(10), tc.y);
     const double m = __hiloint2double((int)((mh >> 12) | 0x3ff00000u), (int)(mh << 20));
     const double r = fma(m, tc.x, -1.0);
-    double q = fma(r, SDE_KC(11), 1.0);                      // -2 log1p(r) = r (-2 + r (1 - 2/3 r)) + O(r^4 / 2)
-    q = fma(q, r, -2.0);
-    const double x = sde_icdf_as_tail(fma(q, r, base), tc.x, base);
-    const int xhi = __double2hiint(x) ^ (~sgn & 0x80000000);                         // p < 0.5 -> -x
+    double x;
+    if (F32SEED) {
+        const double base = fma((double)pos, SDE_KU(13), tc.y);  // 16 x (-2 ln 2 (pos - 33) - 2 ln c): table built with y_scale = 16
+        double q = fma(r, SDE_KC(14), 16.0);
+        q = fma(q, r, -32.0);
+        x = sde_icdf_as_tail_f32seed(fma(q, r, base));
+    } else {
+        const double base = fma((double)pos, SDE_KU(10), tc.y);
+        double q = fma(r, SDE_KC(11), 1.0);                  // -2 log1p(r) = r (-2 + r (1 - 2/3 r)) + O(r^4 / 2)
+        q = fma(q, r, -2.0);
+        x = sde_icdf_as_tail(fma(q, r, base), tc.x, base);
+    }
+    const int xhi = __double2hiint(x) ^ (int)(neg & 0x80000000u);
     return __hiloint2double(xhi, __double2loint(x));
+}
+__device__ __forceinline__ double sde_icdf_fast_j32w(sde_u32 j, sde_u32 neg, sde_u32 tab_lane) {
+    return sde_icdf_fast_j32w_t<SDE_ICDF_F32SEED>(j, neg, tab_lane);
+}
+__device__ __forceinline__ double sde_icdf_normal_fast_k32w(sde_u32 k, sde_u32 tab_lane) {
+    const int sgn = (int)k >> 31;                            // all ones when p >= 0.5
+    sde_u32 j;                                               // w = min(p, 1-p) = j * 2^-33, j = 2 (k ^ sgn) + 1
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(k ^ (sde_u32)sgn));
+    return sde_icdf_fast_j32w(j, ~(sde_u32)sgn, tab_lane);   // p < 0.5 -> -x
+}
+// Sign-folded entry (persistent kernel, SDE_RES_FOLD): y = k ^ ((k >>s 31) & 0x7fffffff) arrives ready made — bit 31 is
+// the sign bit of k, bits 30..0 are those of k ^ sgn — so 2 y + 1 (mod 2^32) is j and ~y carries the negation flag.
+__device__ __forceinline__ double sde_icdf_normal_fast_y32w(sde_u32 y, sde_u32 tab_lane) {
+    sde_u32 j;
+    asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(y));
+    return sde_icdf_fast_j32w(j, ~y, tab_lane);
 }
 
 // General f64 entry (Cranley–Patterson compat mode, stand-alone kernel): p in [0, 1).

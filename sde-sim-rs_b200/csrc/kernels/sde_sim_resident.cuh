@@ -18,8 +18,21 @@
 // load/store phases of different warps overlap instead of marching in step; no tile prologue/epilogue code,
 // no staged prefetch registers.
 //
+// Work split: a CTA only takes items of ONE class c = blockIdx.x & 3 (item = 4 m + c), so every warp of the CTA has
+// the same step shift gamma, and the Sobol words a 4-step group reads are stored so that they are ONE aligned 128-bit
+// shared-memory load per table:
+//     lane table   [quad][lane][4]   word of dimension d at quad (d + off) >> 2, component (d + off) & 3
+//     warp part    [d + off]         (broadcast load)
+// with off = (-gamma K) mod 4 chosen per CTA so that the dimensions of a group start on a quad boundary.  The grid is
+// a multiple of 4 CTAs (lower.cpp / engine.cpp).
+// SDE_RES_FOLD (digital shift + fast inverse normal, all factors Wiener): both tables hold the words in sign-folded form
+//     y = x ^ ((x >>s 31) & 0x7fffffff)        bit 31 = (p >= 1/2), bits 30..0 = the bits of min(p, 1 - p)
+// which is GF(2)-linear in x like the Sobol map itself, so the XOR of the two table words IS the folded integer of the
+// path's uniform: the inverse normal starts from it with no sign-mask / conditional-complement instructions.
+//
 // Macros expected from the generated prelude (as for sde_sim_kernel.cuh) plus
 //   SDE_S                          number of steps S = T - 1 (compile time: the plan owns the time grid)
+//   SDE_ALL_WIENER                 1 when every stochastic factor is a Wiener increment
 // Requires SDE_RNG in {2, 3} (Sobol with XOR digital shift / raw), SDE_OUT == 0, SDE_UNR == 4.
 #pragma once
 #include "sde_sim_common.cuh"
@@ -38,7 +51,10 @@
 #endif
 
 #ifndef SDE_RES_GRP
-#define SDE_RES_GRP 4                          /* steps per unrolled group: 4 or 8 (whole 32-byte sectors) */
+#define SDE_RES_GRP 4                          /* steps per unrolled group = one 32-byte sector per lane and process */
+#endif
+#if SDE_RES_GRP != 4
+#error "sde_sim_resident.cuh: the row heads / tails assume groups of 4 steps"
 #endif
 #ifndef SDE_RES_PIPE
 #define SDE_RES_PIPE 1                         /* draws of group g+1 overlap the state updates of group g */
@@ -53,20 +69,37 @@
 #ifndef SDE_ST_HINT
 #define SDE_ST_HINT ""                         /* cache operator of the group stores (tuning: ".cs", ".wt", ".cg") */
 #endif
+#ifndef SDE_ALL_WIENER
+#define SDE_ALL_WIENER 0
+#endif
+#ifndef SDE_RES_FOLD
+#define SDE_RES_FOLD (SDE_RNG == 2 && SDE_ICDF == 1 && !SDE_NEEDS_U0 && SDE_ALL_WIENER)
+#endif
 #define SDE_NW (SDE_BLOCK / 32)
 #define SDE_SK (SDE_S * SDE_K)
 #define SDE_STEP_LD (4 + SDE_NSLOT)
-#define SDE_BW_LD ((SDE_SK + 3) & ~3)
+#define SDE_NQ ((SDE_SK + 3 + 3) / 4)          /* quads of 4 dimensions, with room for the per-CTA offset 0..3 */
+#define SDE_BW_LD (SDE_NQ * 4)
+#define SDE_QPG ((SDE_RES_GRP * SDE_K) / 4)    /* quads per step group */
 #define SDE_NIB_LD ((SDE_SK + 31) & ~31)      /* leading dimension of the transposed nibble table */
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
 #ifndef SDE_ICDF_WIDE
 #define SDE_ICDF_WIDE 0                         /* 1: 1024-entry log table (128 KB), set by the lowering when it fits */
 #endif
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1) ? ((SDE_ICDF_WIDE ? SDE_ICDF_WIDE_DOUBLES : SDE_ICDF_TABLE_DOUBLES) * 8) : 0)
-#define SDE_SMEM_LANE_BYTES (SDE_SK * 32 * 4)
+#define SDE_SMEM_LANE_BYTES (SDE_NQ * 32 * 16)
 #define SDE_SMEM_STEP_BYTES (SDE_S * SDE_STEP_LD * 8)
 #define SDE_SMEM_BW_BYTES (SDE_NW * SDE_BW_LD * 4)
 #define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_LANE_BYTES + SDE_SMEM_BW_BYTES)
+
+// sign-folded form of a 32-bit word (see SDE_RES_FOLD above); the identity when the plan does not fold
+__device__ __forceinline__ sde_u32 sde_res_fold(sde_u32 x) {
+#if SDE_RES_FOLD
+    return x ^ ((sde_u32)((int)x >> 31) & 0x7fffffffu);
+#else
+    return x;
+#endif
+}
 
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
     extern __shared__ double4 sde_smem_raw[];
@@ -82,6 +115,16 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     const int warp = tid >> 5;
     constexpr int S = SDE_S, T = SDE_S + 1;
 
+    const sde_u64 first_n = prm.scen_offset + 5ull;           // Sobol::new(..).skip(5)  (sobol.rs:17)
+    const sde_u64 n_base = first_n & ~127ull;
+    const sde_u64 n_blocks = (first_n + prm.n_paths - n_base + 127ull) >> 7;   // blocks of 128 paths = items per class
+    // this CTA's item class and the step shift all of its rows share: row s starts at element s T P, and the group that
+    // starts at step gamma writes elements from (gamma + 1) P on — P (s T + gamma + 1) = 0 (mod 4) puts that on a
+    // 32-byte boundary (the output base is 32-byte aligned); s = n - first_n = cls - first_n (mod 4) for every lane
+    const int cls = (int)(blockIdx.x & 3u);
+    const int gamma = (4 - (int)((((long long)(n_base + (sde_u64)cls) - (long long)first_n) * T + 1) & 3)) & 3;
+    const int off = (4 - ((gamma * SDE_K) & 3)) & 3;          // (gamma K + off) = 0 (mod 4): groups start on a quad
+
     // ---- CTA prologue: the tables every path of every item reads
 #if SDE_ICDF == 1
 #if SDE_ICDF_WIDE
@@ -91,11 +134,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
 #endif
     for (int e = tid; e < SDE_SK * 32; e += SDE_BLOCK) {
+        const int d = e >> 5, l = e & 31;
         sde_u32 v = __ldg(prm.sobol_lane + e);
 #if SDE_RNG == 2
-        v ^= __ldg(prm.xor_masks + (e >> 5));                 // u = ((x ^ mask) + 1/2) 2^-32: one mask per dimension
+        v ^= __ldg(prm.xor_masks + d);                        // u = ((x ^ mask) + 1/2) 2^-32: one mask per dimension
 #endif
-        s_lane[e] = v;
+        const int dd = d + off;
+        s_lane[(((dd >> 2) << 5) + l) * 4 + (dd & 3)] = sde_res_fold(v);
     }
     for (int e = tid; e < S; e += SDE_BLOCK) {
         const double t_cur = __ldg(prm.times + e), t_next = __ldg(prm.times + e + 1);
@@ -112,24 +157,27 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     __syncthreads();
 
     sde_u32* const my_bw = s_bw + warp * SDE_BW_LD;
-    const sde_u32* const my_lane = s_lane + lane;
+    // shared-window byte addresses of the words of "step 0" in this lane's column of the lane table / in this warp's part
+    // (explicit ld.shared.v4.u32 in draw_group): the quad of step tg is 128 K tg / 4 K tg bytes further on
+    const sde_u32 lane_t0 = (sde_u32)__cvta_generic_to_shared(s_lane + lane * 4) + (sde_u32)off * 128u;
+    const sde_u32 bw_t0 = (sde_u32)__cvta_generic_to_shared(my_bw) + (sde_u32)off * 4u;
 #if SDE_ICDF == 1
     const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_icdf + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
 #endif
-
-    const sde_u64 first_n = prm.scen_offset + 5ull;           // Sobol::new(..).skip(5)  (sobol.rs:17)
-    const sde_u64 n_base = first_n & ~127ull;
-    const sde_u64 n_items = 4ull * ((first_n + prm.n_paths - n_base + 127ull) >> 7);
-    const sde_u64 item_stride = (sde_u64)gridDim.x * SDE_NW;
+    // word of dimension d: lane part / warp part (scalar accesses: row heads and tails)
+    auto lane_word = [&](const int d) __attribute__((always_inline)) { const int dd = d + off; return s_lane[(((dd >> 2) << 5) + lane) * 4 + (dd & 3)]; };
+    auto bw_word = [&](const int d) __attribute__((always_inline)) { return my_bw[d + off]; };
 
     double x0[SDE_P];
 #pragma unroll
     for (int p = 0; p < SDE_P; ++p) x0[p] = __ldg(prm.x0 + p);
     const double t_first = __ldg(prm.times);
+    const sde_u64 m_stride = (sde_u64)(gridDim.x >> 2) * SDE_NW;
 
 #pragma unroll 1
-    for (sde_u64 item = (sde_u64)blockIdx.x * SDE_NW + warp; item < n_items; item += item_stride) {
-        const sde_u64 n0 = n_base + ((item >> 2) << 7) + (item & 3ull);
+    for (sde_u64 m = (sde_u64)(blockIdx.x >> 2) * SDE_NW + warp; m < n_blocks; m += m_stride) {
+        // item = 32 paths n = n0 + 4 lane of block m
+        const sde_u64 n0 = n_base + (m << 7) + (sde_u64)cls;
         const sde_u64 n = n0 + (sde_u64)(4 * lane);
         const bool valid = (n >= first_n) && (n - first_n < prm.n_paths);
         if (!__any_sync(0xffffffffu, valid)) continue;
@@ -142,17 +190,17 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             // prm.sobol_nib arrives transposed for this kernel, [8][16][SDE_NIB_LD] (dimension fastest): the 32 lanes of
             // a load read 32 consecutive dimensions of one (nibble position, nibble value) row — one 128-byte line
             const sde_u32 g = (sde_u32)n0 ^ ((sde_u32)n0 >> 1);
-            sde_u32 off[8];
+            sde_u32 noff[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) off[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
+            for (int q = 0; q < 8; ++q) noff[q] = (sde_u32)(q * 16 + ((g >> (4 * q)) & 15u)) * SDE_NIB_LD + lane;
             // all loads of up to 8 chunks (256 dimensions) in flight at once: one L2 round trip per item instead of one
             // per pair of chunks (folding ahead inside the step loop was measured slower: it costs the loop 30 registers)
 #pragma unroll 8
             for (int d = 0; d < SDE_NIB_LD; d += 32) {
                 sde_u32 v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = __ldg(prm.sobol_nib + off[q] + d);
-                if (d + lane < SDE_SK) my_bw[d + lane] = ((v[0] ^ v[1]) ^ (v[2] ^ v[3])) ^ ((v[4] ^ v[5]) ^ (v[6] ^ v[7]));
+                for (int q = 0; q < 8; ++q) v[q] = __ldg(prm.sobol_nib + noff[q] + d);
+                if (d + lane < SDE_SK) my_bw[d + lane + off] = sde_res_fold(((v[0] ^ v[1]) ^ (v[2] ^ v[3])) ^ ((v[4] ^ v[5]) ^ (v[6] ^ v[7])));
             }
         }
 #endif
@@ -163,16 +211,59 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         double ct = t_first;
 #pragma unroll
         for (int p = 0; p < SDE_P; ++p) { row[p] = x0[p]; cache[p] = x0[p]; }
-        // this path's rows [T][P].  Pad lanes (they only exist in the first and last item of a launch) are pointed at a
+        // this path's rows [T][P].  Pad lanes (they only exist in the first and last block of a launch) are pointed at a
         // scratch row with the same phase modulo a sector, so the group stores of the step loop need no predicate
         double* const my_row = valid ? prm.out + (size_t)s_local * T * SDE_P
                                      : prm.partials + (size_t)(((long long)s_local * T * SDE_P) & 3);
-        // step shift of this warp: the group that starts at step gamma writes elements from (gamma + 1) P on, and
-        // P (s T + gamma + 1) = 0 (mod 4) puts that on a 32-byte boundary (the output base is 32-byte aligned)
-        const int gamma = __shfl_sync(0xffffffffu, (int)((4 - (int)(((long long)s_local * T + 1) & 3)) & 3), 0);
 
-        // draw_x: uniforms -> normal / Poisson draws of step t.  `flip[k]` is XORed into the Sobol integer of factor k:
-        // zero for the lane's own path, V_d[ctz(n + 1)] for the path that follows it (x_d(n+1) = x_d(n) ^ V_d[ctz(n+1)])
+        // draw_word: the (digitally shifted, possibly sign-folded) 32-bit word of factor k -> normal / Poisson draw
+        auto draw_word = [&](const sde_u32 w, const int k, double& z, double& u0) __attribute__((always_inline)) {
+#if SDE_RES_FOLD
+            // w is the folded integer of p = (x + 1/2) 2^-32: every factor is Wiener, nothing else reads the uniform
+#if SDE_ICDF_WIDE
+            z = sde_icdf_normal_fast_y32w(w, tab_lane);
+#else
+            z = sde_icdf_normal_fast_y32s(w, tab_lane);
+#endif
+            (void)k; (void)u0;
+#elif SDE_RNG == 2
+            const sde_u32 x = w;
+            if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+            // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
+            if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1 && SDE_ICDF_WIDE
+                z = sde_icdf_normal_fast_k32w(x, tab_lane);
+#elif SDE_ICDF == 1
+                z = sde_icdf_normal_fast_k32s(x, tab_lane);
+#elif SDE_ICDF == 2
+                z = sde_icdf_normal_single_k32(x);
+#else
+                z = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
+#endif
+            } else {
+                z = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+            }
+#else
+            {   // raw points: u = x / 2^32 (can be 0: the reference's ln(0) path gives NaN)
+                const double u = (double)w * 2.3283064365386963e-10;
+                if (k == 0) u0 = u;
+                if (sde_factor_is_wiener(k)) {
+#if SDE_ICDF == 1
+                    z = sde_icdf_normal_fast(u, s_icdf, lane);
+#elif SDE_ICDF == 2
+                    z = sde_icdf_normal_single(u);
+#else
+                    z = sde_icdf_normal_reference(u);
+#endif
+                } else {
+                    z = u;
+                }
+            }
+#endif
+        };
+        // draw_x: draws of step t on its own (row heads / tails).  `flip[k]` is XORed into the word of factor k: zero for
+        // the lane's own path, (the folded form of) V_d[ctz(n + 1)] for the path that follows it
+        // (x_d(n+1) = x_d(n) ^ V_d[ctz(n+1)], and folding is linear)
         auto draw_x = [&](const int t, const sde_u32 (&flip)[SDE_KK], double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
             u0 = 0.0;
             zu[0] = 0.0;
@@ -183,40 +274,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
             for (int k = 0; k < SDE_K; ++k) {
                 const int d = t * SDE_K + k;
-                const sde_u32 x = my_bw[d] ^ my_lane[d * 32] ^ flip[k];   // (digitally shifted) 32-bit Sobol integer
-                if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
-#if SDE_RNG == 2
-                // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
-                if (sde_factor_is_wiener(k)) {
-#if SDE_ICDF == 1 && SDE_ICDF_WIDE
-                    zu[k] = sde_icdf_normal_fast_k32w(x, tab_lane);
-#elif SDE_ICDF == 1
-                    zu[k] = sde_icdf_normal_fast_k32s(x, tab_lane);
-#elif SDE_ICDF == 2
-                    zu[k] = sde_icdf_normal_single_k32(x);
-#else
-                    zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
-#endif
-                } else {
-                    zu[k] = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
-                }
-#else
-                {   // raw points: u = x / 2^32 (can be 0: the reference's ln(0) path gives NaN)
-                    const double u = (double)x * 2.3283064365386963e-10;
-                    if (k == 0) u0 = u;
-                    if (sde_factor_is_wiener(k)) {
-#if SDE_ICDF == 1
-                        zu[k] = sde_icdf_normal_fast(u, s_icdf, lane);
-#elif SDE_ICDF == 2
-                        zu[k] = sde_icdf_normal_single(u);
-#else
-                        zu[k] = sde_icdf_normal_reference(u);
-#endif
-                    } else {
-                        zu[k] = u;
-                    }
-                }
-#endif
+                draw_word(bw_word(d) ^ lane_word(d) ^ flip[k], k, zu[k], u0);
             }
         };
         auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
@@ -224,6 +282,35 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
             for (int k = 0; k < SDE_KK; ++k) none[k] = 0u;
             draw_x(t, none, zu, u0);
+        };
+        // draw_group: the draws of the SDE_RES_GRP steps from tg on (tg = gamma mod 4): their words sit in SDE_QPG quads of
+        // either table — one 128-bit load per quad (lane table: conflict free; warp part: broadcast).  Quad q of the lane
+        // table is 512 bytes, of the warp part 16 bytes, and q = (tg K + off) / 4: both addresses are one multiply-add on
+        // the step counter (written as opaque PTX so that they are not turned into extra loop-carried pointers)
+        auto draw_group = [&](const int tg, double (&zu)[SDE_RES_GRP][SDE_KK], double (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
+#ifdef SDE_DEBUG_NOCOMPUTE
+#pragma unroll
+            for (int j = 0; j < SDE_RES_GRP; ++j) { u0[j] = 0.0; zu[j][0] = (double)(tg + j) * 1e-4; }
+            return;
+#endif
+            sde_u32 la, ba;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(la) : "r"(tg), "n"(128 * SDE_K), "r"(lane_t0));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ba) : "r"(tg), "n"(4 * SDE_K), "r"(bw_t0));
+            sde_u32 lw[4 * SDE_QPG], bw[4 * SDE_QPG];
+#pragma unroll
+            for (int i = 0; i < SDE_QPG; ++i) {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lw[4 * i]), "=r"(lw[4 * i + 1]), "=r"(lw[4 * i + 2]), "=r"(lw[4 * i + 3]) : "r"(la + i * 512u) : "memory");
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bw[4 * i]), "=r"(bw[4 * i + 1]), "=r"(bw[4 * i + 2]), "=r"(bw[4 * i + 3]) : "r"(ba + i * 16u) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < SDE_RES_GRP; ++j) {
+                u0[j] = 0.0;
+                zu[j][0] = 0.0;
+#pragma unroll
+                for (int k = 0; k < SDE_K; ++k) draw_word(lw[j * SDE_K + k] ^ bw[j * SDE_K + k], k, zu[j][k], u0[j]);
+            }
         };
         // one step on its own (the <= 3 steps before the first and after the last aligned group)
         auto single = [&](const int t) __attribute__((always_inline)) {
@@ -238,6 +325,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
         };
 
+        (void)single;
         int t = 0;
         const int g_eff = gamma < S ? gamma : S;
 #if SDE_FULL_SECTORS
@@ -275,7 +363,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         for (; t < g_eff; ++t) single(t);
 #endif
         const int n_groups = (S - g_eff) / SDE_RES_GRP;
-        double* dst = my_row + (size_t)(g_eff + 1) * SDE_P;   // 32-byte aligned by the choice of gamma
+        const int t_last = g_eff + n_groups * SDE_RES_GRP;    // end of the grouped steps
+        double* const row1 = my_row + SDE_P;                  // element (tg + 1) P of the row: 32-byte aligned for tg = gamma (mod 4)
 #ifdef SDE_DEBUG_NOSTORE
         const int live = (valid && prm.reserved == 12345) ? 1 : 0;   // profiling aid: group stores predicated off
 #else
@@ -283,7 +372,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         (void)live;
 #endif
         // advance_group: the sequential state updates of one group (rows t+1 .. t+GRP collected in output order) and
-        // their predicated (not branched) full-sector stores: dead lanes only exist in the first and last item
+        // their full-sector stores (pad lanes write the scratch row)
         auto advance_group = [&](const int tg, const double (&zu)[SDE_RES_GRP][SDE_KK], const double (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
             double vals[SDE_RES_GRP * SDE_P];
 #pragma unroll
@@ -292,6 +381,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
             }
+            double* dst;                                      // row1 + tg P (one wide multiply-add on the step counter)
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(dst) : "r"(tg), "n"(8 * SDE_P), "l"(row1));
 #pragma unroll
             for (int q = 0; q < SDE_P * (SDE_RES_GRP / 4); ++q) {
 #if SDE_ST256 && !defined(SDE_DEBUG_NOSTORE)
@@ -307,7 +398,6 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                              ::"l"(dst + 4 * q + 2), "d"(vals[4 * q + 2]), "d"(vals[4 * q + 3]), "r"(live) : "memory");
 #endif
             }
-            dst += SDE_RES_GRP * SDE_P;
         };
 #if SDE_RES_PIPE
         // software pipeline: the state-independent uniform -> normal chains of group g+1 are issued together with the
@@ -315,21 +405,16 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // (two register sets, ping-pong: no copies on the loop back edge)
         if (n_groups > 0) {
             double za[SDE_RES_GRP][SDE_KK], ua[SDE_RES_GRP], zb[SDE_RES_GRP][SDE_KK], ub[SDE_RES_GRP];
-#pragma unroll
-            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, za[j], ua[j]);
-            int left = n_groups - 1;                          // groups whose draws are still to be issued
+            draw_group(t, za, ua);
 #pragma unroll 1
-            for (; left >= 2; left -= 2, t += 2 * SDE_RES_GRP) {
-#pragma unroll
-                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zb[j], ub[j]);
+            for (; t + 3 * SDE_RES_GRP <= t_last; t += 2 * SDE_RES_GRP) {   // the step counter is the only loop-carried integer
+                draw_group(t + SDE_RES_GRP, zb, ub);
                 advance_group(t, za, ua);
-#pragma unroll
-                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + 2 * SDE_RES_GRP + j, za[j], ua[j]);
+                draw_group(t + 2 * SDE_RES_GRP, za, ua);
                 advance_group(t + SDE_RES_GRP, zb, ub);
             }
-            if (left == 1) {
-#pragma unroll
-                for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + SDE_RES_GRP + j, zb[j], ub[j]);
+            if (t + 2 * SDE_RES_GRP <= t_last) {
+                draw_group(t + SDE_RES_GRP, zb, ub);
                 advance_group(t, za, ua);
                 advance_group(t + SDE_RES_GRP, zb, ub);
                 t += 2 * SDE_RES_GRP;
@@ -343,8 +428,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         for (int gi = 0; gi < n_groups; ++gi, t += SDE_RES_GRP) {
             // phase 1: the state-independent uniform -> normal chains of the group (independent instruction streams)
             double zu[SDE_RES_GRP][SDE_KK], u0[SDE_RES_GRP];
-#pragma unroll
-            for (int j = 0; j < SDE_RES_GRP; ++j) draw(t + j, zu[j], u0[j]);
+            draw_group(t, zu, u0);
             advance_group(t, zu, u0);
         }
 #endif
@@ -376,7 +460,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                         sde_u32 flip[SDE_KK];
 #pragma unroll
                         for (int k = 0; k < SDE_K; ++k)       // V_d[b] = nibble-table entry of the single-bit nibble value
-                            flip[k] = __ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k));
+                            flip[k] = sde_res_fold(__ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k)));
                         double zu[SDE_KK], u0;
                         draw_x(j, flip, zu, u0);
                         sde_model_step(row2, cache2, ct2, zu, u0, s_step + j * SDE_STEP_LD);

@@ -67,19 +67,45 @@ extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal(const double
 }
 
 // K3w: the 32-bit front end with the 1024-entry log table of the persistent kernel (128 KB of dynamic shared memory).
-extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal_wide(const double* __restrict__ p, sde_u64 n, double* __restrict__ out) {
+// f32seed = 1: the variant with FP32-unit seeds and quadratic steps (sde_icdf_as_tail_f32seed), through the sign-folded entry.
+extern "C" __global__ void __launch_bounds__(256) sde_k_icdf_normal_wide(const double* __restrict__ p, sde_u64 n, double* __restrict__ out, int f32seed) {
     extern __shared__ double4 s_wide_raw[];
     double* s_table = reinterpret_cast<double*>(s_wide_raw);
-    sde_icdf_wide_table_build(s_table, threadIdx.x, 256, SDE_ICDF_Y_OFFSET_K32);
+    sde_icdf_wide_table_build(s_table, threadIdx.x, 256, SDE_ICDF_Y_OFFSET_K32, f32seed ? 16.0 : 1.0);
     __syncthreads();
     const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_table + 2 * (threadIdx.x & (SDE_ICDF_TABLE_REPL - 1)));
-    for (sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (sde_u64)gridDim.x * 256)
-        out[i] = sde_icdf_normal_fast_k32w((sde_u32)(unsigned long long)(p[i] * 4294967296.0), tab_lane);
+    for (sde_u64 i = (sde_u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (sde_u64)gridDim.x * 256) {
+        const sde_u32 k = (sde_u32)(unsigned long long)(p[i] * 4294967296.0);
+        const sde_u32 y = k ^ ((sde_u32)((int)k >> 31) & 0x7fffffffu);          // sign-folded word (sde_sim_resident.cuh)
+        sde_u32 j;
+        asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(j) : "r"(y));
+        out[i] = f32seed ? sde_icdf_fast_j32w_t<1>(j, ~y, tab_lane) : sde_icdf_fast_j32w_t<0>(j, ~y, tab_lane);
+    }
 }
 
 extern "C" __global__ void sde_k_icdf_poisson(const double* __restrict__ u, const double* __restrict__ lambda, sde_u64 n, double* __restrict__ out) {
     const sde_u64 i = (sde_u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = sde_icdf_poisson(u[i], lambda[i]);
+}
+
+// K8 (merge stage): per-shard (count, mean, M2) triples [n_shards][P][3] -> [P][3], Chan et al., shards in order with
+// separately rounded operations — the same arithmetic, bit for bit, as the host's sde_moments_merge.  Runs on the compute
+// stream right behind the all-gather of the triples (one thread per process; 3 P doubles per shard).
+extern "C" __global__ void __launch_bounds__(128) sde_k_moments_merge(const double* __restrict__ shards, sde_u64 n_shards, int P,
+                                                                       double* __restrict__ out) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        double n = 0.0, mean = 0.0, m2 = 0.0;
+        for (sde_u64 s = 0; s < n_shards; ++s) {
+            const double* b = shards + (s * (sde_u64)P + p) * 3;
+            const double nb = b[0];
+            if (nb == 0.0) continue;
+            const double nn = __dadd_rn(n, nb), dlt = __dsub_rn(b[1], mean), f = __ddiv_rn(nb, nn);
+            m2 = __dadd_rn(__dadd_rn(m2, b[2]), __dmul_rn(__dmul_rn(__dmul_rn(dlt, dlt), n), f));
+            mean = __dadd_rn(mean, __dmul_rn(dlt, f));
+            n = nn;
+        }
+        out[p * 3] = n; out[p * 3 + 1] = mean; out[p * 3 + 2] = m2;
+    }
 }
 
 // ---- microbenchmarks ------------------------------------------------------------------

@@ -28,7 +28,7 @@ from ._ffi import (ARITH_FAST, ARITH_STRICT, DTYPE_F32, DTYPE_F64, ICDF_FAST, IC
                    OUT_PATHS, OUT_TERMINAL, RK_REFERENCE, RK_TEXTBOOK, SCRAMBLE_CP_SHIFT_PER_PATH, SCRAMBLE_NONE,
                    SCRAMBLE_XOR)
 
-__all__ = ["simulate", "simulate_frame", "simulate_devices", "simulate_sharded", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
+__all__ = ["simulate", "simulate_frame", "simulate_devices", "simulate_sharded", "DevicePlans", "merge_moments_device", "parse_equations", "Universe", "Plan", "Filtration", "shard_range", "merge_moments",
            "cuda_available", "version"]
 
 _OUTPUTS = {"paths": OUT_PATHS, "terminal": OUT_TERMINAL, "moments": OUT_MOMENTS}
@@ -369,47 +369,119 @@ def merge_moments(shards: np.ndarray) -> np.ndarray:
     return out
 
 
+class DevicePlans:
+    """One plan per GPU of `devices` behind ONE C call per run (sde_device_plans_create / sde_plan_run_devices): the
+    host-side replacement of rayon's par_iter over scenarios (src/sim/mod.rs:41-43).  Moments are all-gathered over NCCL
+    and Chan-merged on the devices inside that call; `collective` says how ("nccl", "peer" copies, or "none")."""
+
+    def __init__(self, universe: Universe, scheme: str = "euler", rng_method: str = "pseudo", *, devices: Optional[Sequence[int]] = None,
+                 output: str = "paths", layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
+                 arithmetic: str = "strict", rk_variant: str = "reference", dtype: str = "f64", block_threads: int = 0, wide_mma: int = 0):
+        import torch
+
+        self.universe, self.output, self.layout = universe, output, layout
+        self.dtype = "f32" if _pick(_DTYPES, dtype, "dtype") == DTYPE_F32 else "f64"
+        devs = list(range(torch.cuda.device_count())) if devices is None else [int(d) for d in devices]
+        if not devs:
+            raise RuntimeError("Simulation failed: no CUDA device (there is no CPU fallback)")
+        opts = _make_options(device=devs[0], seed=0, scenario_offset=0, output=output, layout=layout, scramble=scramble, icdf=icdf,
+                             arithmetic=arithmetic, rk_variant=rk_variant, dtype=dtype, block_threads=block_threads, wide_mma=wide_mma)
+        h = C.c_void_p()
+        arr = (C.c_int32 * len(devs))(*devs)
+        rc = _ffi.lib().sde_device_plans_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), arr, len(devs), C.byref(h))
+        _ffi.check(rc, prefix_runtime="Simulation failed: ")
+        self._h, self.devices, self.launches, self.collective_ms = h, devs, 0, 0.0
+        self.collective = {0: "none", 1: "nccl", 2: "peer"}[_ffi.lib().sde_device_plans_collective(h)]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _ffi is not None and getattr(_ffi, "_lib", None) is not None:
+            _ffi._lib.sde_device_plans_free(h)
+
+    def run(self, initial_values: Dict[str, float], scenarios: int, *, seed: int = 0, scenario_offset: int = 0):
+        """Returns the per-device CUDA tensors: shard i of the paths / terminal values on device i, or (moments) the merged
+        [P, 3] on every device.  Synchronous (every device has finished)."""
+        import torch
+
+        if scenarios <= 0:
+            raise ValueError("scenarios must be a positive integer")
+        T, P, G = self.universe.time_steps.size, self.universe.num_processes, len(self.devices)
+        tdt = torch.float32 if (self.dtype == "f32" and self.output != "moments") else torch.float64
+        outs = []
+        for i, d in enumerate(self.devices):
+            lo, hi = shard_range(scenarios, i, G)
+            n = hi - lo
+            shape = (P, 3) if self.output == "moments" else ((n, P) if self.output == "terminal" else ((n, T, P) if self.layout == "NTP" else (T, P, n)))
+            outs.append(torch.empty(shape, dtype=tdt, device=f"cuda:{d}"))
+        for d in self.devices:
+            torch.cuda.synchronize(d)                            # the library launches on its own streams
+        ptrs = (C.c_void_p * G)(*[t.data_ptr() if t.numel() else None for t in outs])
+        names, vals, n_init = Plan._init_arrays(initial_values)
+        nl, cms = C.c_int(0), C.c_double(0.0)
+        rc = _ffi.lib().sde_plan_run_devices(self._h, names, vals.ctypes.data_as(C.c_void_p), n_init, scenarios, seed & (2**64 - 1),
+                                             scenario_offset, ptrs, C.byref(nl), C.byref(cms))
+        _ffi.check(rc, prefix_runtime="Simulation failed: ")
+        self.launches += nl.value
+        self.collective_ms = cms.value
+        return outs
+
+
+_DEVICE_PLAN_CACHE: Dict[tuple, DevicePlans] = {}
+
+
 def simulate_devices(processes_equations, time_steps, scenarios, initial_values, rng_method="pseudo", scheme="euler", *,
                      devices: Optional[Sequence[int]] = None, seed: Optional[int] = None, output: str = "paths", **kw):
-    """ONE process driving several GPUs of the box (the convenience for scripts; under torchrun use `simulate_sharded`):
-    device i of `devices` (default: all visible) simulates `shard_range(scenarios, i, len(devices))` with that scenario
-    offset — disjoint Sobol index ranges / ChaCha keys, no data-path exchange.  All launches are issued before any device
-    is synchronised.  Returns the list of per-device `Filtration` shards (paths / terminal values stay on their GPU, in
-    scenario order) or, for output="moments", one `Filtration` with the Chan-merged moments."""
+    """ONE process driving several GPUs of the box through one C call (sde_plan_run_devices; under torchrun use
+    `simulate_sharded`): device i of `devices` (default: all visible) simulates `shard_range(scenarios, i, len(devices))` —
+    disjoint Sobol index ranges / ChaCha keys, no data-path exchange; all launches are issued before any device is
+    synchronised.  Returns the list of per-device `Filtration` shards (paths / terminal values stay on their GPU, in
+    scenario order) or, for output="moments", one `Filtration` with the moments merged on the devices (NCCL all-gather
+    + Chan-merge kernel)."""
     import torch
 
     if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
         raise ValueError("scenarios must be a positive integer")
     devs = list(range(torch.cuda.device_count())) if devices is None else [int(d) for d in devices]
-    if not devs:
-        raise RuntimeError("Simulation failed: no CUDA device (there is no CPU fallback)")
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
-    plans = [_cached_plan(list(processes_equations), time_steps, scheme, rng_method, output=output, device=d, **kw) for d in devs]
+    ts = np.ascontiguousarray(np.asarray(time_steps, dtype=np.float64))
+    key = (tuple(processes_equations), ts.tobytes(), scheme, rng_method, tuple(devs), output, tuple(sorted(kw.items())))
+    plans = _DEVICE_PLAN_CACHE.get(key)
+    if plans is None:
+        if len(_DEVICE_PLAN_CACHE) > 8:
+            _DEVICE_PLAN_CACHE.clear()
+        plans = _DEVICE_PLAN_CACHE[key] = DevicePlans(Universe(list(processes_equations), ts), scheme, rng_method, devices=devs, output=output, **kw)
+    outs = plans.run(dict(initial_values), int(scenarios), seed=seed)
+    uni, layout = plans.universe, kw.get("layout", "NTP")
+    if output == "moments":
+        return Filtration(outs[0], uni.time_steps, uni.process_names, output=output, layout="NTP", scenario_offset=0, seed=seed)
     shards = []
-    for i, (d, plan) in enumerate(zip(devs, plans)):
+    for i, t in enumerate(outs):
         lo, hi = shard_range(int(scenarios), i, len(devs))
-        if hi == lo:
-            continue
-        with torch.cuda.device(d):
-            values = plan.run(dict(initial_values), hi - lo, seed=seed, scenario_offset=lo)       # asynchronous on d's stream
-        shards.append(Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output,
-                                 layout=kw.get("layout", "NTP"), scenario_offset=lo, seed=seed))
-    for d in set(devs):
-        torch.cuda.synchronize(d)
-    if output != "moments":
-        return shards
-    merged = merge_moments(np.stack([s.to_numpy() for s in shards]))
-    first = shards[0]
-    return Filtration(torch.from_numpy(merged).to(first.values.device), first.time_steps, first.process_names, output=output,
-                      layout="NTP", scenario_offset=0, seed=seed)
+        if hi > lo:
+            shards.append(Filtration(t, uni.time_steps, uni.process_names, output=output, layout=layout, scenario_offset=lo, seed=seed))
+    return shards
+
+
+def merge_moments_device(shards):
+    """[n_shards, P, 3] CUDA tensor of (count, mean, M2) triples -> [P, 3] on the same device, by the library's merge
+    kernel on the current stream (same arithmetic, bit for bit, as `merge_moments`)."""
+    import torch
+
+    assert shards.is_cuda and shards.dtype == torch.float64 and shards.dim() == 3 and shards.shape[2] == 3
+    shards = shards.contiguous()
+    out = torch.empty(shards.shape[1:], dtype=torch.float64, device=shards.device)
+    dev = shards.device.index
+    _ffi.check(_ffi.lib().sde_moments_merge_device(dev, C.c_void_p(shards.data_ptr()), shards.shape[0], shards.shape[1],
+                                                   C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
 
 
 def simulate_sharded(processes_equations, time_steps, scenarios, initial_values, rng_method="pseudo", scheme="euler", *,
                      seed: int = 0, output: str = "moments", **kw) -> Filtration:
     """One process per GPU (torch.distributed already initialised): every rank simulates its scenario range;
-    moments are all-gathered (3·P doubles per rank over NCCL/NVLink) and merged identically on every rank;
-    paths / terminal values stay resident on their GPU."""
+    moments are all-gathered (3·P doubles per rank over NCCL/NVLink) and merged by the library's device kernel on the
+    same stream — identically on every rank, no host hop; paths / terminal values stay resident on their GPU."""
     import torch
     import torch.distributed as dist
 
@@ -431,8 +503,7 @@ def simulate_sharded(processes_equations, time_steps, scenarios, initial_values,
         res = Filtration(torch.zeros(shape, dtype=dt, device=f"cuda:{dev}" if torch.cuda.is_available() else "cpu"),
                          uni.time_steps, uni.process_names, output=output, layout=kw.get("layout", "NTP"), scenario_offset=lo, seed=seed)
     if output == "moments" and world > 1:
-        gathered = [torch.empty_like(res.values) for _ in range(world)]
-        dist.all_gather(gathered, res.values)
-        merged = merge_moments(torch.stack(gathered).cpu().numpy())
-        res.values = torch.from_numpy(merged).to(res.values.device)
+        gathered = torch.empty((world,) + tuple(res.values.shape), dtype=res.values.dtype, device=res.values.device)
+        dist.all_gather_into_tensor(gathered, res.values)
+        res.values = merge_moments_device(gathered) if gathered.is_cuda else torch.from_numpy(merge_moments(gathered.numpy()))
     return res

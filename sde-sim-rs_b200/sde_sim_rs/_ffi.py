@@ -79,6 +79,21 @@ SIGNATURES = {
     "sde_result_values_device": (_vp, [_vp]),
     "sde_result_values_host": (_i32, [_vp, _vp, _sz]),
     "sde_result_kernel_ms": (_dbl, [_vp]),
+    "sde_result_process_name": (C.c_char_p, [_vp, _sz]),
+    "sde_result_times": (_i32, [_vp, _vp, _sz]),
+    "sde_result_scenario_offset": (_u64, [_vp]),
+    "sde_result_device": (_i32, [_vp]),
+    "sde_result_output": (_i32, [_vp]),
+    "sde_result_moments": (_i32, [_vp, _vp]),
+    "sde_shard_range": (None, [_u64, _sz, _sz, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sde_device_plans_create": (_i32, [_vp, C.c_char_p, C.c_char_p, _popt, C.POINTER(C.c_int32), _sz, C.POINTER(_vp)]),
+    "sde_device_plans_free": (None, [_vp]),
+    "sde_device_plans_count": (_sz, [_vp]),
+    "sde_device_plans_device": (_i32, [_vp, _sz]),
+    "sde_device_plans_collective": (_i32, [_vp]),
+    "sde_plan_run_devices": (_i32, [_vp, _strs, _vp, _sz, _u64, _u64, _u64, C.POINTER(_vp), _pint, C.POINTER(_dbl)]),
+    "sde_simulate_devices": (_i32, [_vp, _strs, _vp, _sz, _u64, C.c_char_p, C.c_char_p, _popt, C.POINTER(C.c_int32), _sz, C.POINTER(_vp)]),
+    "sde_moments_merge_device": (_i32, [_i32, _vp, _sz, _sz, _vp, _vp]),
     "sde_sobol_points": (_i32, [_i32, _u32, _u64, _u64, _vp]),
     "sde_joe_kuo_params": (_i32, [_u32, _vp, _vp]),
     "sde_chacha8_u64": (_i32, [_i32, _u64, _sz, _vp]),
@@ -89,6 +104,7 @@ SIGNATURES = {
     "sde_last_error": (C.c_char_p, []),
     "sde_version": (C.c_char_p, []),
     "sde_cuda_available": (_i32, []),
+    "sde_device_count": (_i32, []),
 }
 
 _lib = None

@@ -73,6 +73,58 @@ int main(int argc, char** argv) {
     }
     printf("checks: %s\n", ok ? "ok" : "FAILED");
     printf("sum=%.17g\nterminal_mean=%.17g\nfirst_path_terminal=%.17g\n", sum, sum_t / (double)n, v[rt - 1]);
+    /* what else the reference's frame carries (filtration.rs:108-113): names, times, first scenario */
+    {
+        double* tt = (double*)malloc(rt * sizeof(double));
+        if (sde_result_times(res, tt, rt) != SDE_OK || tt[0] != times[0] || tt[rt - 1] != times[rt - 1]) ok = 0;
+        if (strcmp(sde_result_process_name(res, 0), "X1") != 0 || sde_result_scenario_offset(res) != 0 || sde_result_output(res) != SDE_OUT_PATHS) ok = 0;
+        free(tt);
+    }
+
+    /* ---- the same run sharded over every GPU of the box in ONE call (rayon's par_iter over scenarios, sim/mod.rs:41-43):
+     *      the union of the shards must be bit-identical to the single-device result; then the moments, merged on the devices */
+    {
+        const int n_dev = sde_device_count();
+        sde_result** shards = (sde_result**)calloc((size_t)n_dev, sizeof(sde_result*));
+        rc = sde_simulate_devices(u, names, vals, 1, n, scheme, rng, &opt, NULL, (size_t)n_dev, shards);
+        if (rc != SDE_OK) { printf("simulate_devices failed rc=%d: %s\n", rc, sde_last_error()); return 1; }
+        size_t at = 0;
+        int same = 1;
+        for (int i = 0; i < n_dev; ++i) {
+            uint64_t lo = 0, hi = 0, sn = 0;
+            sde_shard_range(n, (size_t)i, (size_t)n_dev, &lo, &hi);
+            sde_result_shape(shards[i], &sn, NULL, NULL);
+            if (sn != hi - lo || sde_result_scenario_offset(shards[i]) != lo || sde_result_device(shards[i]) != i) same = 0;
+            const size_t se = sde_result_num_elems(shards[i]);
+            if (se) {
+                double* sv = (double*)malloc(se * sizeof(double));
+                if (sde_result_values_host(shards[i], sv, se) != SDE_OK || memcmp(sv, v + at, se * sizeof(double)) != 0) same = 0;
+                free(sv);
+            }
+            at += se;
+            sde_result_free(shards[i]);
+        }
+        if (at != ne) same = 0;
+        printf("devices: %d shard union %s\n", n_dev, same ? "bit-identical" : "DIFFERS");
+        if (!same) ok = 0;
+
+        sde_options mo = opt;
+        mo.output = SDE_OUT_MOMENTS;
+        rc = sde_simulate_devices(u, names, vals, 1, n, scheme, rng, &mo, NULL, (size_t)n_dev, shards);
+        if (rc != SDE_OK) { printf("simulate_devices(moments) failed rc=%d: %s\n", rc, sde_last_error()); return 1; }
+        double mom[3] = {0, 0, 0}, mean = sum_t / (double)n, m2 = 0.0;
+        for (size_t s = 0; s < (size_t)n; ++s) { const double d = v[s * rt + rt - 1] - mean; m2 += d * d; }
+        int mom_ok = 1;
+        for (int i = 0; i < n_dev; ++i) {                      /* every device holds the merged triple */
+            if (sde_result_moments(shards[i], mom) != SDE_OK) mom_ok = 0;
+            if (mom[0] != (double)n || fabs(mom[1] / mean - 1.0) > 1e-13 || fabs(mom[2] / m2 - 1.0) > 1e-10) mom_ok = 0;
+            sde_result_free(shards[i]);
+        }
+        printf("devices: merged moments %s (count=%.0f mean=%.17g)\n", mom_ok ? "ok" : "FAILED", mom[0], mom[1]);
+        if (!mom_ok) ok = 0;
+        free(shards);
+    }
+    printf("all checks: %s\n", ok ? "ok" : "FAILED");
     free(v);
     sde_result_free(res);
     sde_universe_free(u);

@@ -46,7 +46,8 @@ def test_header_is_c99_and_library_links_from_c(consumer):
 def test_c_caller_matches_python_mirror_and_oracle(consumer, oracle, rng, scheme):
     N, D, seed = 500, 32, 7
     r = _run(consumer, N, D, seed, rng, scheme)
-    assert r.returncode == 0 and "checks: ok" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "checks: ok" in r.stdout and "all checks: ok" in r.stdout, r.stdout + r.stderr
+    assert "shard union bit-identical" in r.stdout and "merged moments ok" in r.stdout, r.stdout
     vals = {k: float(v) for k, v in re.findall(r"^(sum|terminal_mean|first_path_terminal)=(\S+)$", r.stdout, re.M)}
     kw = {"scramble": "xor"} if rng == "sobol" else {}
     got = S.simulate(GBM_EQ, grid(252, D), N, {"X1": 1.0}, rng, scheme, seed=seed, **kw).to_numpy()

@@ -104,7 +104,8 @@ def test_icdf_fast_k32_front_end_tolerance(oracle):
                         rng.integers(0, 2**12, size=20_000, dtype=np.uint64)])          # deep left tail
     p = (k.astype(np.float64) + 0.5) * 2.0**-32
     ref = oracle.icdf_normal(p)
-    for mode, name in ((2, "128-entry table"), (5, "1024-entry table")):      # tiled kernel / persistent kernel
+    # tiled kernel / persistent kernel / persistent kernel with FP32-unit seeds + quadratic steps (sign-folded entry)
+    for mode, name in ((2, "128-entry table"), (5, "1024-entry table"), (6, "1024-entry table, FP32-unit seeds")):
         got = _icdf_dev(p, mode)
         err = np.abs(got - ref)
         print("k32 icdf,", name, "max abs err", err.max(), "at k =", int(k[np.argmax(err)]))

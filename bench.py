@@ -12,8 +12,12 @@ so scaling is weak and `value` is the aggregate path-steps/s.
 
 The JSON line carries `roofline` (HBM write bound; algorithmic bytes = 8*P per path-step incl. the t0 row),
 `cpu_baseline` (the CPU oracle on a bounded sample, on this box's host cores), `e2e` (same workload through
-the C-ABI host-buffer call: chunked simulate + D2H into pinned host memory inside the timed region),
-`clocks` and `gpu_launches`.
+the C-ABI host-buffer call: chunked simulate + D2H into pinned host memory inside the timed region, with its own
+roofline against the measured pinned D2H rate), `clocks`, `gpu_launches`, and beside the headline:
+`timed_output_parity` (rows of the timed output against the CPU oracle), `plan_create_ms` (cached / cold NVRTC),
+`configs` (every other BASELINE.json config on this GPU, a few launches each: C1, C2 with the reference's cp_shift
+scramble, C2 in [T][P][N] layout, C3 full paths and terminal, C4 moments, C5 per GPU) and `c5_strong` (BASELINE C5:
+2^33 paths x 365 steps split over the N GPUs, the NCCL all-gather + device Chan merge of the moments inside the timed region).
 """
 from __future__ import annotations
 
@@ -40,6 +44,24 @@ SEED = 42
 METRIC = "path_steps_per_sec"
 UNIT = "path-steps/s"
 WORKLOAD = "C2: 1-D GBM Euler-Maruyama, RQMC scrambled Sobol (XOR digital shift), 2^24 paths x 252 steps per GPU, full-path f64 output [N,253,1]"
+
+
+HESTON_EQ = ["dS = ( 0.05 * S ) * dt + ( max(v, 0.0)^0.5 * S ) * dW1",
+             "dv = ( 2.0 * (0.04 - v) ) * dt + ( -0.21 * max(v, 0.0)^0.5 ) * dW1 + ( 0.2142428528562855 * max(v, 0.0)^0.5 ) * dW2"]
+
+
+def basket_equations(n_assets=64, rho=0.5):
+    """C4: correlated GBM basket, correlation through shared dW names with Cholesky loadings."""
+    import numpy as np
+
+    corr = np.full((n_assets, n_assets), rho)
+    np.fill_diagonal(corr, 1.0)
+    L = np.linalg.cholesky(corr)
+    eqs = []
+    for i in range(n_assets):
+        sig = 0.1 + 0.2 * i / max(n_assets - 1, 1)
+        eqs.append(f"dS{i} = ( 0.05 * S{i} ) * dt + " + " + ".join(f"( {sig * L[i, j]:.17g} * S{i} ) * dW{j + 1}" for j in range(i + 1)))
+    return eqs, {f"S{i}": 100.0 for i in range(n_assets)}
 
 
 def _measured_peak_gbs():
@@ -147,6 +169,149 @@ def cpu_reference_leg(sample_paths: int, repeats: int = 1):
     return sample_paths * D / best, _host_threads(), best
 
 
+
+def timed_output_parity(out, n, offset):
+    """Rows of the buffer the timed region just wrote against the CPU oracle (the checker, not the thing measured):
+    the first 256, 256 in the middle and the last 256 scenarios; fast tier => <= 1e-11 relative."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    orc.build()
+    U = orc.Universe(GBM_EQ, TIMES)
+    worst, rows = 0.0, 0
+    for lo in (0, n // 2 + 77, n - 256):
+        lo = max(0, min(lo, n - 256))
+        cnt = min(256, n - lo)
+        ref = orc.simulate(U, INIT, cnt, "euler", "sobol", seed=SEED, scramble="xor", scenario_offset=offset + lo, nthreads=2)
+        got = out[lo:lo + cnt].cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(got - ref) / np.abs(ref))))
+        rows += cnt
+    return {"max_rel_err": worst, "rows_checked": rows, "tolerance": 1e-11, "ok": bool(worst <= 1e-11),
+            "against": "CPU oracle (oracle/sde_oracle.cpp) on the same scenario indices"}
+
+
+def _time_plan(torch, plan, init, n, out, reps, **kw):
+    plan.run(init, n, seed=SEED, out=out, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan.run(init, n, seed=SEED, out=out, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def plan_create_times(S, dev):
+    """Plan creation: from the ahead-of-time cubin cache (what a deployment sees) and cold (NVRTC sm_100a compile of a model the
+    cache has never seen: the headline model with a perturbed coefficient)."""
+    t0 = time.perf_counter()
+    p = S.Plan(S.Universe(GBM_EQ, TIMES), "euler", "sobol", output="paths", scramble="xor", icdf="fast", arithmetic="fast", device=dev)
+    cached_ms, was_cached = (time.perf_counter() - t0) * 1e3, p.prelowered
+    eq = [f"dX1 = ( 0.05 * X1 ) * dt + ( 0.1{int(time.time() * 1e3) % 100000:05d} * X1) * dW1"]
+    t0 = time.perf_counter()
+    S.Plan(S.Universe(eq, TIMES), "euler", "sobol", output="paths", scramble="xor", icdf="fast", arithmetic="fast", device=dev)
+    return {"from_cache_ms": cached_ms, "cache_hit": bool(was_cached), "cold_nvrtc_ms": (time.perf_counter() - t0) * 1e3,
+            "what": "sde_plan_create of the C2 plan: lowering + cubin (disk cache / NVRTC --gpu-architecture=sm_100a) + table upload"}
+
+
+def config_legs(S, torch, dev, holder, peak_gbs, dfma_tflops):
+    """Every other BASELINE.json config on this GPU: one warm launch + a few timed ones each (CUDA events, device-resident
+    output).  Full-path configs against the HBM write roofline (8 P bytes per path-step, t0 row included); terminal /
+    moment configs against the measured DFMA peak with the flop model of SURVEY.md 8(d).  `holder[0]` is the 34 GB
+    buffer of the headline leg: reused by the 2^24 x 253 legs, released before the 67 GB of C3's full paths."""
+    legs = {}
+    fast = dict(icdf="fast", arithmetic="fast")
+
+    def hbm(n, t_len, p_, ms):
+        gbs = n * t_len * p_ * 8 / (ms * 1e-3) * 1e-9
+        return {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs}
+
+    def fp64(rate, flop):
+        tf = rate * flop * 1e-12
+        return {"bound": "fp64", "achieved": tf, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": (tf / dfma_tflops) if dfma_tflops else None,
+                "flop_model_per_path_step": flop}
+
+    def leg(name, eqs, times, init, n, scheme, rng, reps, roof, reuse=False, **kw):
+        plan = S.Plan(S.Universe(eqs, times), scheme, rng, device=dev, **kw)
+        shape = plan.output_shape(n)
+        numel = 1
+        for d_ in shape:
+            numel *= d_
+        o = holder[0].view(-1)[:numel].view(shape) if reuse else torch.empty(shape, dtype=torch.float64, device=f"cuda:{dev}")
+        ms = _time_plan(torch, plan, init, n, o, reps)
+        steps = len(times) - 1
+        rate = n * steps / (ms * 1e-3)
+        legs[name] = {"value": rate, "unit": UNIT, "ms": ms, "paths": n, "steps": steps, "launches_timed": reps, "roofline": roof(n, steps, ms, rate)}
+        del o, plan
+        torch.cuda.empty_cache()
+
+    g252, g365, g1000 = TIMES, [k / 365 for k in range(366)], [k / 1000 for k in range(1001)]
+    n2 = 1 << 24
+    heston_init = {"S": 100.0, "v": 0.04}
+    leg("C1_gbm_euler_pseudo_10k_full_paths", GBM_EQ, g252, INIT, 10_000, "euler", "pseudo", 5, lambda n, s_, ms, r: hbm(n, s_ + 1, 1, ms), output="paths", **fast)
+    leg("C2_cp_shift_per_path_full_paths", GBM_EQ, g252, INIT, n2, "euler", "sobol", 3, lambda n, s_, ms, r: hbm(n, s_ + 1, 1, ms), reuse=True,
+        output="paths", scramble="cp_shift_per_path", **fast)
+    leg("C2_layout_TPN_full_paths", GBM_EQ, g252, INIT, n2, "euler", "sobol", 3, lambda n, s_, ms, r: hbm(n, s_ + 1, 1, ms), reuse=True,
+        output="paths", layout="TPN", scramble="xor", **fast)
+    holder[0] = None
+    torch.cuda.empty_cache()
+    leg("C3_heston_rk_sobol_4M_x_1000_full_paths", HESTON_EQ, g1000, heston_init, 1 << 22, "runge-kutta", "sobol", 2,
+        lambda n, s_, ms, r: hbm(n, s_ + 1, 2, ms), output="paths", scramble="xor", **fast)
+    leg("C3_heston_rk_sobol_4M_x_1000_terminal", HESTON_EQ, g1000, heston_init, 1 << 22, "runge-kutta", "sobol", 2,
+        lambda n, s_, ms, r: fp64(r, 100), output="terminal", scramble="xor", **fast)
+    beq, binit = basket_equations(64)
+    leg("C4_basket64_euler_sobol_1M_x_252_moments", beq, g252, binit, 1 << 20, "euler", "sobol", 2,
+        lambda n, s_, ms, r: fp64(r, 5632), output="moments", scramble="xor", **fast)
+    leg("C5_gbm_euler_pseudo_2p30_x_365_moments_per_gpu", GBM_EQ, g365, INIT, 1 << 30, "euler", "pseudo", 1,
+        lambda n, s_, ms, r: fp64(r, 26), output="moments", **fast)
+    return legs
+
+
+def c5_strong_leg(S, torch, dist, world, rank, dev, total_paths):
+    """BASELINE C5: `total_paths` x 365 steps of GBM terminal-only MC split over the `world` GPUs (strong scaling); every rank
+    reduces its shard to (count, mean, M2), the triples are all-gathered over NCCL and Chan-merged by the library's
+    device kernel — all inside the timed region (CUDA events, max over ranks).  collective_ms: the all-gather + merge
+    alone, timed on its own afterwards."""
+    g365 = [k / 365 for k in range(366)]
+    kw = dict(seed=2024, output="moments", icdf="fast", arithmetic="fast", device=dev)
+    S.simulate_sharded(GBM_EQ, g365, min(total_paths, world << 20), INIT, "pseudo", "euler", **kw)      # plan, communicator
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = S.simulate_sharded(GBM_EQ, g365, total_paths, INIT, "pseudo", "euler", **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{dev}")
+    coll_ms = 0.0
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g = torch.empty((world,) + tuple(res.values.shape), dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_gather_into_tensor(g, res.values)
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(g, res.values)
+            S.merge_moments_device(g)
+        c1.record()
+        torch.cuda.synchronize()
+        coll_ms = c0.elapsed_time(c1) / 5
+    ms = float(t.item())
+    m = res.to_numpy()[0]
+    mu, sig, dt = 0.05, 0.1, 1.0 / 365
+    mean = (1 + mu * dt) ** 365
+    var = ((1 + mu * dt) ** 2 + sig * sig * dt) ** 365 - mean**2
+    return {"value": total_paths * 365 / (ms * 1e-3), "unit": UNIT, "ms": ms, "total_paths": total_paths, "steps": 365, "n_gpus": world,
+            "scaling": "strong", "collective": "ncclAllGather of 3 doubles per rank + device Chan merge (sde_moments_merge_device), inside the timed region",
+            "collective_ms": coll_ms, "count": float(m[0]), "mean": float(m[1]), "mean_closed_form": mean,
+            "mean_err_in_standard_errors": abs(float(m[1]) - mean) / (var / total_paths) ** 0.5}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -197,6 +362,7 @@ def run_gpu(args):
     N, S_, P, T = args.paths, D, 1, D + 1
     offset = rank * N
 
+    plan_ms = plan_create_times(S, dev) if rank == 0 else None
     plan = S.Plan(S.Universe(GBM_EQ, TIMES), "euler", "sobol", output="paths", layout="NTP", scramble="xor",
                   icdf=args.icdf, arithmetic=args.arithmetic, device=dev, tile_steps=args.tile_steps, block_threads=args.block)
     out = torch.empty((N, T, P), dtype=torch.float64, device=f"cuda:{dev}")
@@ -249,15 +415,40 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
 
-    # spot parity of what was just timed: first/last rows vs closed-form sanity (finite, positive, t0 row = x0)
-    chk = out[:4, :, 0].cpu()
-    assert torch.isfinite(chk).all() and bool((chk[:, 0] == 1.0).all())
+    # parity of what was just timed: the buffer the last timed launch wrote, against the CPU oracle on the same scenarios
+    parity = None
+    if rank == 0:
+        plan.run(INIT, N, seed=SEED, scenario_offset=offset, out=out)       # (the isolated launches above wrote the same values)
+        torch.cuda.synchronize()
+        parity = timed_output_parity(out, N, offset)
+        assert parity["ok"], parity
+    if world > 1:
+        dist.barrier()
+
+    # ---- the other BASELINE configs on this GPU (rank 0; the other ranks wait) and C5 strong-scaled over all ranks
+    configs, peaks = None, None
+    holder = [out]
+    del out
+    if not args.no_configs:
+        if rank == 0:
+            import ctypes as C
+
+            fill, dfma, ffma = C.c_double(0), C.c_double(0), C.c_double(0)
+            S._ffi.check(S._ffi.lib().sde_measure_peaks(dev, C.byref(fill), C.byref(dfma), C.byref(ffma)))
+            peaks = {"fill_gbs": fill.value, "dfma_tflops": dfma.value, "ffma_tflops": ffma.value,
+                     "how": "sde_measure_peaks: 8 GiB pure-write fill; 8 independent FMA chains per thread (own kernels, this box, this run)"}
+            configs = config_legs(S, torch, dev, holder, _measured_peak_gbs()[0], dfma.value)
+        if world > 1:
+            dist.barrier()
+    holder[0] = None
+    torch.cuda.empty_cache()
+    c5 = None
+    if not args.no_configs:
+        c5 = c5_strong_leg(S, torch, dist, world, rank, dev, args.c5_paths)
 
     # ---- end-to-end leg: host buffers through the C-ABI (sde_plan_run_host), D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        del out
-        torch.cuda.empty_cache()
         nbytes = N * T * P * 8
         try:
             host = torch.empty((N, T, P), dtype=torch.float64, pin_memory=True)
@@ -278,9 +469,26 @@ def run_gpu(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
             assert float(host[0, 0, 0]) == 1.0 and bool(torch.isfinite(host[-1]).all())
+            # the ceiling of this leg: pinned device -> host copies on this box (4 GiB blocks, all ranks at once like the leg itself)
+            probe = torch.empty(1 << 29, dtype=torch.float64, device=f"cuda:{dev}")
+            hview = host.view(-1)[: 1 << 29]
+            hview.copy_(probe)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                hview.copy_(probe, non_blocking=True)
+            barrier()
+            d2h = torch.tensor([3 * (1 << 32) / (time.perf_counter() - t0) * 1e-9], dtype=torch.float64, device=f"cuda:{dev}")
+            if world > 1:
+                dist.all_reduce(d2h, op=dist.ReduceOp.MIN)
+            d2h_gbs = float(d2h.item())
+            del probe
             e2e = {"value": world * N * S_ / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * P + 8 * S_ * 1,
                    "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": k2,
-                   "api": "sde_plan_run_host (C-ABI, pinned host output, 512 MiB chunks, copy overlapped with compute)"}
+                   "api": "sde_plan_run_host (C-ABI, pinned host output, 512 MiB chunks, copy overlapped with compute)",
+                   "roofline": {"bound": "pinned D2H over PCIe", "achieved": nbytes / dt * 1e-9, "peak": d2h_gbs, "unit": "GB/s per GPU",
+                                "frac": nbytes / dt * 1e-9 / d2h_gbs,
+                                "how": f"peak = slowest rank's 4 GiB pinned cudaMemcpyAsync D2H rate with all {world} rank(s) copying at once"}}
             del host
 
     if rank == 0:
@@ -308,6 +516,7 @@ def run_gpu(args):
                        "l2_policy": "each step writes 33.96 GB >> 126 MB L2 (no flush needed)",
                        "parallelism": f"paths sharded over {world} GPU(s), disjoint Sobol index ranges"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "timed_output_parity": parity, "plan_create_ms": plan_ms, "device_peaks": peaks, "configs": configs, "c5_strong": c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -328,6 +537,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs beside the headline (other BASELINE configs, C5 strong scaling)")
+    ap.add_argument("--c5-paths", type=int, default=1 << 33, help="total paths of the C5 strong-scaling leg (BASELINE: 2^33)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 21)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

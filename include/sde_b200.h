@@ -223,6 +223,10 @@ int sde_simulate_devices(const sde_universe* u, const char* const* init_names, c
  * (device kernel; host output [count][dims]).  Replaces sobol::Sobol::<f64>::new(dims,
  * JoeKuoD6::extended()) as used at src/rng/sobol.rs:15-25. */
 int sde_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out);
+/* The uniforms the reference's Sobol mode feeds a path (device kernel; host output [count][dims]):
+ * u[i][d] = fract(raw_d(point first_scenario + i + 5) + shift_d), shift = f64 draws of ChaCha8Rng::seed_from_u64(seed +
+ * scenario) — SobolRng::new + RandomShiftScrambler (src/rng/sobol.rs:35-53,62-79), scenario seeding src/sim/mod.rs:56. */
+int sde_sobol_cp_shift_uniforms(int device, uint32_t dims, uint64_t seed, uint64_t first_scenario, uint64_t count, double* h_out);
 /* Joe–Kuo parameters shipped with the library (for checking against an independent copy). */
 int sde_joe_kuo_params(uint32_t dims, uint32_t* poly /*[dims]*/, uint32_t* minit /*[dims][18]*/);
 /* u64 / f64 stream of ChaCha8Rng::seed_from_u64(seed) (src/rng/pseudo.rs:18,25), generated on the device. */

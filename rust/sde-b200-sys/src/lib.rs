@@ -113,6 +113,7 @@ extern "C" {
     pub fn sde_simulate_devices(u: *const sde_universe, init_names: *const *const c_char, init_vals: *const c_double, n_init: usize, n_scenarios: u64, scheme: *const c_char, rng_method: *const c_char, opt: *const sde_options, devices: *const i32, n_devices: usize, out: *mut *mut sde_result) -> c_int;
     // ---- building blocks
     pub fn sde_sobol_points(device: c_int, dims: u32, first: u64, count: u64, h_out: *mut u64) -> c_int;
+    pub fn sde_sobol_cp_shift_uniforms(device: c_int, dims: u32, seed: u64, first_scenario: u64, count: u64, h_out: *mut c_double) -> c_int;
     pub fn sde_joe_kuo_params(dims: u32, poly: *mut u32, minit: *mut u32) -> c_int;
     pub fn sde_chacha8_u64(device: c_int, seed: u64, n: usize, h_out: *mut u64) -> c_int;
     pub fn sde_icdf_normal(device: c_int, mode: c_int, h_p: *const c_double, n: usize, h_out: *mut c_double) -> c_int;

@@ -344,6 +344,9 @@ int sde_moments_merge_device(int device, const double* d_shards, size_t n_shards
 int sde_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out) {
     return guarded([&] { util_sobol_points(device, dims, first, count, h_out); });
 }
+int sde_sobol_cp_shift_uniforms(int device, uint32_t dims, uint64_t seed, uint64_t first_scenario, uint64_t count, double* h_out) {
+    return guarded([&] { util_sobol_cp_uniforms(device, dims, seed, first_scenario, count, h_out); });
+}
 int sde_joe_kuo_params(uint32_t dims, uint32_t* poly, uint32_t* minit) {
     return guarded([&] { joe_kuo_params(dims, poly, minit); });
 }

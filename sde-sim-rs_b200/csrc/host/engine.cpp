@@ -396,7 +396,7 @@ namespace {
 struct UtilModule {
     CUmodule mod = nullptr;
     CUfunction sobol = nullptr, chacha = nullptr, icdf = nullptr, icdf_wide = nullptr, poisson = nullptr, fill = nullptr, dfma = nullptr, ffma = nullptr,
-               merge = nullptr;
+               merge = nullptr, cp_uniforms = nullptr;
 };
 UtilModule& util_module(int device) {
     static std::mutex mu;
@@ -417,6 +417,7 @@ UtilModule& util_module(int device) {
         cu_check(d.cuModuleGetFunction(&m.dfma, m.mod, "sde_k_dfma"), "sde_k_dfma");
         cu_check(d.cuModuleGetFunction(&m.ffma, m.mod, "sde_k_ffma"), "sde_k_ffma");
         cu_check(d.cuModuleGetFunction(&m.merge, m.mod, "sde_k_moments_merge"), "sde_k_moments_merge");
+        cu_check(d.cuModuleGetFunction(&m.cp_uniforms, m.mod, "sde_k_sobol_cp_uniforms"), "sde_k_sobol_cp_uniforms");
     }
     return m;
 }
@@ -441,6 +442,20 @@ void util_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count
     void* args[] = {&pV, &pL, &dims, &n_base, &first, &count, &po};
     launch1d(m.sobol, grid, 256, 256 * 8 * 4, args);
     cu_check(d.cuMemcpyDtoH(h_out, dout.ptr(), count * dims * 8), "cuMemcpyDtoH");
+}
+
+void util_sobol_cp_uniforms(int device, uint32_t dims, uint64_t seed, uint64_t first_scenario, uint64_t count, double* h_out) {
+    if (dims == 0 || count == 0) return;
+    if (first_scenario + 5 + count > (1ull << 32)) throw ExprError{"sobol point index exceeds 2^32"};
+    UtilModule& m = util_module(device);
+    std::vector<uint32_t> V, lane;
+    sobol_tables(dims, V, lane);
+    DeviceBuffer dV, dout(count * dims * 8);
+    dV.upload(V.data(), V.size() * 4);
+    CUdeviceptr pV = dV.ptr(), po = dout.ptr();
+    void* args[] = {&pV, &dims, &seed, &first_scenario, &count, &po};
+    launch1d(m.cp_uniforms, (count + 127) / 128, 128, 0, args);
+    cu_check(driver().cuMemcpyDtoH(h_out, dout.ptr(), count * dims * 8), "cuMemcpyDtoH");
 }
 
 void util_chacha8_u64(int device, uint64_t seed, size_t n, uint64_t* h_out) {

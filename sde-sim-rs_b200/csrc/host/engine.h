@@ -113,6 +113,7 @@ void moments_merge_device(int device, const double* d_shards, size_t n_shards, s
 
 // ---- stand-alone building blocks (ahead-of-time cubin)
 void util_sobol_points(int device, uint32_t dims, uint64_t first, uint64_t count, uint64_t* h_out);
+void util_sobol_cp_uniforms(int device, uint32_t dims, uint64_t seed, uint64_t first_scenario, uint64_t count, double* h_out);
 void util_chacha8_u64(int device, uint64_t seed, size_t n, uint64_t* h_out);
 void util_icdf_normal(int device, int mode, const double* h_p, size_t n, double* h_out);
 void util_icdf_poisson(int device, const double* h_u, const double* h_lambda, size_t n, double* h_out);

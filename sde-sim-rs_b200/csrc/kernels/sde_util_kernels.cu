@@ -34,6 +34,31 @@ extern "C" __global__ void __launch_bounds__(256) sde_k_sobol_points(const sde_u
     }
 }
 
+// K1s: the uniforms of the reference's Sobol mode, u[i][d] = fract(x_d(n) + shift_d) for scenario first_scenario + i
+// (n = scenario + 5): raw point rendered as x / 2^32 (exact: the points only touch the top 32 bits), shift_d = f64 draw #d of
+// ChaCha8Rng::seed_from_u64(seed + scenario) (src/rng/sobol.rs:45-47,67-76; src/sim/mod.rs:56) — the same expression the
+// fused kernel evaluates for SDE_RNG == 1, on its own for the bit-exact test.
+extern "C" __global__ void __launch_bounds__(128) sde_k_sobol_cp_uniforms(const sde_u32* __restrict__ V, sde_u32 dims, sde_u64 seed,
+                                                                          sde_u64 first_scenario, sde_u64 count, double* __restrict__ out) {
+    const sde_u64 i = (sde_u64)blockIdx.x * 128 + threadIdx.x;
+    if (i >= count) return;
+    const sde_u64 s = first_scenario + i;
+    SdeChaCha8Stream cha;
+    cha.init(seed + s);
+    for (sde_u32 d0 = 0; d0 < dims; d0 += 8) {
+        cha.refill();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const sde_u32 d = d0 + q;
+            if (d < dims) {
+                const sde_u32 x = sde_sobol_point32(V + (size_t)d * 32, (sde_u32)(s + 5ull));
+                const double v = (double)x * 2.3283064365386963e-10 + (double)(long long)cha.bits53(q) * 1.1102230246251565e-16;
+                out[i * dims + d] = (v >= 1.0) ? v - 1.0 : v;
+            }
+        }
+    }
+}
+
 // K2: first n u64 outputs of ChaCha8Rng::seed_from_u64(seed); thread i produces block i.
 extern "C" __global__ void sde_k_chacha8_u64(sde_u64 seed, sde_u64 n, sde_u64* __restrict__ out) {
     const sde_u64 b = (sde_u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -308,20 +308,48 @@ def _cached_plan(equations, time_steps, scheme, rng_method, **kw) -> Plan:
     return plan
 
 
+_EXTENSIONS = ("seed", "output", "layout", "scramble", "icdf", "arithmetic", "rk_variant", "device", "scenario_offset", "dtype")
+
+
 def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
              initial_values: Dict[str, float], rng_method: str = "pseudo", scheme: str = "euler", *,
-             seed: Optional[int] = None, output: str = "paths", layout: str = "NTP",
-             scramble: str = "cp_shift_per_path", icdf: str = "reference", arithmetic: str = "strict",
-             rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0,
-             dtype: str = "f64") -> Filtration:
+             frame="auto", **ext):
     """Drop-in for sde_sim_rs.simulate (src/py_binding.rs:10-18; defaults as in python/sde_sim_rs/sde_sim_rs.pyi:11-12).
 
-    Keyword-only extensions: `seed` (the reference draws a fresh OS-entropy seed per call,
-    src/sim/mod.rs:28-29 — so does this when seed is None), `output` paths|terminal|moments, `layout`,
-    `scramble` cp_shift_per_path (reference behaviour) | xor | none, `icdf` reference|fast|single,
-    `arithmetic` strict|fast, `rk_variant` reference|textbook, `device`, `scenario_offset`, `dtype` f64|f32
-    (f32: state, arithmetic and stored values in single precision; needs arithmetic="fast").
+    Called like the reference — the six reference arguments only — it returns what the reference returns: the long
+    DataFrame `scenario:i32, time:f64, process_name:str, value:f64` in (scenario, time, process) order
+    (src/py_binding.rs:51-55, src/filtration.rs:108-113): a polars frame where polars is importable, else pandas.
+
+    Keyword-only extensions: `seed` (the reference draws a fresh OS-entropy seed per call, src/sim/mod.rs:28-29 — so does
+    this when seed is None), `output` paths|terminal|moments, `layout`, `scramble` cp_shift_per_path (reference
+    behaviour) | xor | none, `icdf` reference|fast|single, `arithmetic` strict|fast, `rk_variant` reference|textbook,
+    `device`, `scenario_offset`, `dtype` f64|f32 (f32: state, arithmetic and stored values in single precision; needs
+    arithmetic="fast").  With any of them the result is a `Filtration` (the dense value tensor, resident on the GPU) unless
+    frame=True; frame=False always returns the `Filtration`.
     """
+    unknown = [k for k in ext if k not in _EXTENSIONS]
+    if unknown:
+        raise TypeError(f"simulate() got unexpected keyword argument(s) {unknown}; extensions are {list(_EXTENSIONS)}")
+    if frame not in (True, False, "auto"):
+        raise ValueError("frame must be True, False or 'auto'")
+    want_frame = (len(ext) == 0) if frame == "auto" else bool(frame)
+    res = _simulate_filtration(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme, **ext)
+    if not want_frame:
+        return res
+    if res.output != "paths":
+        raise ValueError("frame=True needs output='paths' (the reference's frame holds every row)")
+    try:
+        return res.to_polars()
+    except ImportError:
+        return res.to_pandas()
+
+
+def _simulate_filtration(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
+                         initial_values: Dict[str, float], rng_method: str = "pseudo", scheme: str = "euler", *,
+                         seed: Optional[int] = None, output: str = "paths", layout: str = "NTP",
+                         scramble: str = "cp_shift_per_path", icdf: str = "reference", arithmetic: str = "strict",
+                         rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0,
+                         dtype: str = "f64") -> Filtration:
     if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
         raise ValueError("scenarios must be a positive integer")                      # py_binding.rs:20-24
     if seed is None:
@@ -342,11 +370,7 @@ def simulate_frame(processes_equations: Sequence[str], time_steps: Sequence[floa
     src/filtration.rs:108-113) — a polars frame where polars is importable (what pyo3-polars hands back), a pandas
     frame otherwise.  `simulate` itself returns the dense GPU tensor wrapped in a `Filtration`; this is the
     convenience for scripts written against the reference package."""
-    res = simulate(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme, **kw)
-    try:
-        return res.to_polars()
-    except ImportError:
-        return res.to_pandas()
+    return simulate(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme, frame=True, **kw)
 
 
 # ---------------------------------------------------------------- multi-GPU helpers
@@ -490,8 +514,8 @@ def simulate_sharded(processes_equations, time_steps, scenarios, initial_values,
         raise ValueError("scenarios must be a positive integer")                      # every rank raises: no collective entered
     lo, hi = shard_range(scenarios, rank, world)
     if hi > lo:
-        res = simulate(processes_equations, time_steps, hi - lo, initial_values, rng_method, scheme, seed=seed,
-                       output=output, scenario_offset=lo, **kw)
+        res = _simulate_filtration(processes_equations, time_steps, hi - lo, initial_values, rng_method, scheme, seed=seed,
+                                   output=output, scenario_offset=lo, **kw)
     else:
         # fewer scenarios than ranks: this rank owns none, but it still enters the collective with a zero-count triple
         uni = Universe(list(processes_equations), time_steps)

@@ -95,6 +95,7 @@ SIGNATURES = {
     "sde_simulate_devices": (_i32, [_vp, _strs, _vp, _sz, _u64, C.c_char_p, C.c_char_p, _popt, C.POINTER(C.c_int32), _sz, C.POINTER(_vp)]),
     "sde_moments_merge_device": (_i32, [_i32, _vp, _sz, _sz, _vp, _vp]),
     "sde_sobol_points": (_i32, [_i32, _u32, _u64, _u64, _vp]),
+    "sde_sobol_cp_shift_uniforms": (_i32, [_i32, _u32, _u64, _u64, _u64, _vp]),
     "sde_joe_kuo_params": (_i32, [_u32, _vp, _vp]),
     "sde_chacha8_u64": (_i32, [_i32, _u64, _sz, _vp]),
     "sde_icdf_normal": (_i32, [_i32, _i32, _vp, _sz, _vp]),

@@ -42,6 +42,17 @@ def test_sobol_points_match_scipy_directly():
     assert np.array_equal(got, qmc.Sobol(d=64, scramble=False, bits=64).random(128))
 
 
+@pytest.mark.parametrize("dims,seed,first,count", [(252, 42, 0, 300), (504, 7, 1000, 64), (2000, 2**63 + 5, 4091, 16), (3, 0, 2**24 - 5, 10)])
+def test_cp_shift_per_path_uniforms_bit_exact(oracle, dims, seed, first, count):
+    # the reference's Sobol mode (SobolRng::new + RandomShiftScrambler, src/rng/sobol.rs:35-53,62-79): u = fract(x_n[d] + ChaCha8(seed + s).f64[d])
+    out = np.zeros((count, dims), dtype=np.float64)
+    _ffi.check(_ffi.lib().sde_sobol_cp_shift_uniforms(0, dims, seed, first, count, out.ctypes.data_as(C.c_void_p)))
+    U = oracle.Universe(["dA = ( 1.0 ) * dW1"], np.arange(dims + 1, dtype=np.float64))
+    ref = oracle.uniforms(U, count, "sobol", seed=seed, scramble="cp_shift_per_path", scenario_offset=first).reshape(count, dims)
+    assert np.array_equal(out, ref)
+    assert out.min() >= 0.0 and out.max() < 1.0
+
+
 @pytest.mark.parametrize("seed,n", [(0, 64), (42, 1000), (2**64 - 1, 17), (123456789, 8)])
 def test_chacha8_stream_bit_exact(oracle, seed, n):
     out = np.zeros(n, dtype=np.uint64)

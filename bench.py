@@ -265,6 +265,8 @@ def config_legs(S, torch, dev, holder, peak_gbs, dfma_tflops):
     leg("C4_basket64_euler_sobol_1M_x_252_moments", beq, g252, binit, 1 << 20, "euler", "sobol", 2,
         lambda n, s_, ms, r: fp64(r, 5632), output="moments", scramble="xor", **fast)
     leg("C5_gbm_euler_pseudo_2p30_x_365_moments_per_gpu", GBM_EQ, g365, INIT, 1 << 30, "euler", "pseudo", 1,
+        lambda n, s_, ms, r: fp64(r, 26), output="moments", generator="philox", **fast)
+    leg("C5_same_with_the_reference_chacha8_stream", GBM_EQ, g365, INIT, 1 << 30, "euler", "pseudo", 1,
         lambda n, s_, ms, r: fp64(r, 26), output="moments", **fast)
     return legs
 
@@ -275,7 +277,7 @@ def c5_strong_leg(S, torch, dist, world, rank, dev, total_paths):
     device kernel — all inside the timed region (CUDA events, max over ranks).  collective_ms: the all-gather + merge
     alone, timed on its own afterwards."""
     g365 = [k / 365 for k in range(366)]
-    kw = dict(seed=2024, output="moments", icdf="fast", arithmetic="fast", device=dev)
+    kw = dict(seed=2024, output="moments", icdf="fast", arithmetic="fast", device=dev, generator="philox")
     S.simulate_sharded(GBM_EQ, g365, min(total_paths, world << 20), INIT, "pseudo", "euler", **kw)      # plan, communicator
     torch.cuda.synchronize()
     if world > 1:
@@ -307,7 +309,8 @@ def c5_strong_leg(S, torch, dist, world, rank, dev, total_paths):
     mean = (1 + mu * dt) ** 365
     var = ((1 + mu * dt) ** 2 + sig * sig * dt) ** 365 - mean**2
     return {"value": total_paths * 365 / (ms * 1e-3), "unit": UNIT, "ms": ms, "total_paths": total_paths, "steps": 365, "n_gpus": world,
-            "scaling": "strong", "collective": "ncclAllGather of 3 doubles per rank + device Chan merge (sde_moments_merge_device), inside the timed region",
+            "scaling": "strong", "generator": "philox (Philox4x32-10: statistical parity with the reference's ChaCha8 stream, tests/test_gpu_philox.py)",
+            "collective": "ncclAllGather of 3 doubles per rank + device Chan merge (sde_moments_merge_device), inside the timed region",
             "collective_ms": coll_ms, "count": float(m[0]), "mean": float(m[1]), "mean_closed_form": mean,
             "mean_err_in_standard_errors": abs(float(m[1]) - mean) / (var / total_paths) ** 0.5}
 

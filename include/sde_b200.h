@@ -67,6 +67,12 @@ enum sde_scramble {
                                            (what README.md:13 describes): u = ((x ^ mask) + 1/2) * 2^-32                     */
     SDE_SCRAMBLE_NONE = 2
 };
+enum sde_generator {
+    SDE_GEN_CHACHA8 = 0,    /* the reference's stream: ChaCha8Rng::seed_from_u64(seed + s) f64 draws (src/rng/pseudo.rs:14-31), bit-exact */
+    SDE_GEN_PHILOX = 1      /* Philox4x32-10, counter = (scenario, draw block), 32-bit uniforms (w + 1/2) 2^-32: not in the reference —
+                               a cheaper counter-based stream for the pseudo-random MC path, which has to agree with the reference
+                               statistically only; rng_method != "sobol" only */
+};
 enum sde_icdf {
     SDE_ICDF_REFERENCE = 0, /* A&S 26.2.23 exactly as src/proc/increment.rs:161-179, IEEE log/sqrt/div, no contraction */
     SDE_ICDF_FAST = 1,      /* same formula; table-driven log + one-step cubic sqrt/div in f64; |dz| <= 5e-13 vs REFERENCE */
@@ -113,6 +119,7 @@ typedef struct sde_options {
                                * terminal values or moments):
                                * 0 = auto (FP64 tensor-core kernel sde_sim_wide.cuh when the model qualifies); 1 = off (time-tiled
                                * kernel); 2 = required (plan creation fails when the model does not qualify)                      */
+    int32_t generator;        /* enum sde_generator: the pseudo-random stream of rng_method != "sobol" (default: the reference's)  */
 } sde_options;
 
 void sde_options_default(sde_options* o);

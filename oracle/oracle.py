@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsde_oracle.so")
 
-RNG_PSEUDO, RNG_SOBOL_CP_SHIFT, RNG_SOBOL_XOR, RNG_SOBOL_RAW, RNG_INJECT = 0, 1, 2, 3, 4
+RNG_PSEUDO, RNG_SOBOL_CP_SHIFT, RNG_SOBOL_XOR, RNG_SOBOL_RAW, RNG_INJECT, RNG_PHILOX = 0, 1, 2, 3, 4, 5
 SCHEME_EULER, SCHEME_RK, SCHEME_RK_TEXTBOOK = 0, 1, 2
 
 
@@ -50,6 +50,9 @@ def lib():
         L.orc_icdf_normal_array.argtypes = [vp, sz, vp]
         L.orc_icdf_poisson.argtypes = [dbl, dbl]
         L.orc_icdf_poisson.restype = u64
+        L.orc_philox4x32_10.argtypes = [vp, vp, vp]
+        L.orc_philox_uniform.argtypes = [u64, u64, u64]
+        L.orc_philox_uniform.restype = dbl
         L.orc_xor_uniform.argtypes = [u64, u64]
         L.orc_xor_uniform.restype = dbl
         L.orc_last_error.restype = C.c_char_p
@@ -147,6 +150,18 @@ def icdf_poisson(u: float, lam: float) -> int:
     return int(lib().orc_icdf_poisson(u, lam))
 
 
+def philox4x32_10(ctr, key) -> np.ndarray:
+    c = np.ascontiguousarray(np.asarray(ctr, dtype=np.uint32))
+    k = np.ascontiguousarray(np.asarray(key, dtype=np.uint32))
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_ptr(c), _ptr(k), _ptr(out))
+    return out
+
+
+def philox_uniform(seed: int, scenario: int, draw: int) -> float:
+    return float(lib().orc_philox_uniform(seed & (2**64 - 1), scenario, draw))
+
+
 def xor_uniform(x: int, mask: int) -> float:
     return float(lib().orc_xor_uniform(x, mask))
 
@@ -193,7 +208,7 @@ class Universe:
 def simulate(universe: Universe, initial_values: dict, scenarios: int, scheme: str = "euler",
              rng_method: str = "pseudo", *, seed: int = 0, scramble: str = "cp_shift_per_path",
              scenario_offset: int = 0, inject: np.ndarray | None = None, nthreads: int = 0,
-             textbook_rk: bool = False) -> np.ndarray:
+             textbook_rk: bool = False, generator: str = "chacha8") -> np.ndarray:
     """sim::simulate restated (src/sim/mod.rs:20-92) -> dense [N, T, P] f64."""
     T, P, K = universe.times.size, universe.P, universe.K
     S = T - 1
@@ -212,6 +227,8 @@ def simulate(universe: Universe, initial_values: dict, scenarios: int, scheme: s
         mode = {"cp_shift_per_path": RNG_SOBOL_CP_SHIFT, "xor": RNG_SOBOL_XOR, "none": RNG_SOBOL_RAW}[scramble]
         if S * K > 0:
             V = sobol_direction_numbers(S * K)
+    elif generator == "philox":
+        mode = RNG_PHILOX                                   # not in the reference: the engine's counter-based MC tier
     else:
         mode = RNG_PSEUDO                                   # any other string -> pseudo (src/sim/mod.rs:65)
     names = list(initial_values)
@@ -225,10 +242,14 @@ def simulate(universe: Universe, initial_values: dict, scenarios: int, scheme: s
 
 
 def uniforms(universe: Universe, scenarios: int, rng_method: str, *, seed: int = 0,
-             scramble: str = "cp_shift_per_path", scenario_offset: int = 0) -> np.ndarray:
+             scramble: str = "cp_shift_per_path", scenario_offset: int = 0, generator: str = "chacha8") -> np.ndarray:
     """The u[s][t][k] stream a run would consume (for building injected-normal inputs)."""
     S, K = universe.times.size - 1, universe.K
     out = np.zeros((scenarios, S, K), dtype=np.float64)
+    if rng_method != "sobol" and generator == "philox":
+        for s in range(scenarios):
+            out[s] = np.array([philox_uniform(seed, s + scenario_offset, i) for i in range(S * K)]).reshape(S, K)
+        return out
     if rng_method != "sobol":
         for s in range(scenarios):
             out[s] = chacha8_f64(s + scenario_offset + seed, S * K).reshape(S, K)

@@ -777,6 +777,29 @@ static void rk_iteration(Filtration& F, const Universe& U, int t, Rng& rng, cons
     for (int p : U.alg_idx) F.set(t + 1, p, F.eval(U.procs[p].alg, nxt));       // :101-106
 }
 
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the generator of Random123 and
+// cuRAND's curandStatePhilox4_32_10): NOT in the reference — the counter-based stream of the engine's generator="philox"
+// tier, which north_star only requires to agree STATISTICALLY with the reference's pseudo mode.  Restated here so that the
+// device stream is held bit-exactly (known answers of Random123's kat_vectors in tests/test_oracle_philox.py).
+static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// draw #i of scenario sg: word i & 3 of block (lo32(sg), hi32(sg), i >> 2, 0) keyed by the seed's two words;
+// uniform = (word + 1/2) 2^-32 in (0, 1) — the same 32-bit form as the digital-shift Sobol uniforms
+static inline double philox_uniform(uint64_t seed, uint64_t sg, uint64_t i) {
+    const uint32_t ctr[4] = {(uint32_t)sg, (uint32_t)(sg >> 32), (uint32_t)(i >> 2), 0u}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t w[4];
+    philox4x32_10(ctr, key, w);
+    return ((double)w[i & 3] + 0.5) * (1.0 / 4294967296.0);
+}
+
 // src/sim/mod.rs:20-92 with explicit seed and deterministic point<->path map.
 static int simulate(const Universe& U, const std::vector<std::pair<std::string, double>>& init,
                     uint64_t N, const SimOptions& opt, double* out /* [N][T][P] */, std::string* err) {
@@ -829,7 +852,9 @@ static int simulate(const Universe& U, const std::vector<std::pair<std::string, 
         } else {
             auto* r = new TableRng; r->K = K; r->values.resize(dims);
             uint64_t n = sg + 5;                           // sobol.rs:17 skip(5) + single-thread order
-            if (opt.rng_mode == 1) {                       // SobolRng::new + RandomShiftScrambler, sobol.rs:35-78
+            if (opt.rng_mode == 5) {                       // generator = "philox": counter-based, no Sobol point
+                for (size_t d = 0; d < dims; ++d) r->values[d] = philox_uniform(opt.seed, sg, d);
+            } else if (opt.rng_mode == 1) {                // SobolRng::new + RandomShiftScrambler, sobol.rs:35-78
                 ChaCha8F64 g(sg + opt.seed);
                 for (size_t d = 0; d < dims; ++d) {
                     double rawv = (double)point_direct(opt.sobol_V + d * 64, n) * (1.0 / 18446744073709551616.0);
@@ -888,6 +913,8 @@ void orc_icdf_normal_array(const double* p, size_t n, double* out) {
     for (size_t i = 0; i < n; ++i) out[i] = orc::icdf_normal(p[i]);
 }
 uint64_t orc_icdf_poisson(double u, double lambda) { return orc::icdf_poisson(u, lambda); }
+void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { orc::philox4x32_10(ctr, key, out); }
+double orc_philox_uniform(uint64_t seed, uint64_t scenario, uint64_t draw) { return orc::philox_uniform(seed, scenario, draw); }
 double orc_xor_uniform(uint64_t x, uint64_t mask) { return orc::xor_uniform(x, mask); }
 
 static thread_local std::string g_err;

@@ -39,6 +39,8 @@ pub const SDE_ARITH_STRICT: i32 = 0;
 pub const SDE_ARITH_FAST: i32 = 1;
 pub const SDE_DTYPE_F64: i32 = 0;
 pub const SDE_DTYPE_F32: i32 = 1;
+pub const SDE_GEN_CHACHA8: i32 = 0;
+pub const SDE_GEN_PHILOX: i32 = 1;
 pub const SDE_RK_REFERENCE: i32 = 0;
 pub const SDE_RK_TEXTBOOK: i32 = 1;
 
@@ -63,6 +65,7 @@ pub struct sde_options {
     pub ntp_direct: i32,
     pub dtype: i32,
     pub wide_mma: i32,
+    pub generator: i32,
 }
 
 extern "C" {

@@ -62,7 +62,9 @@ PlanOptions plan_options(const Universe& u, const char* scheme, const char* rng_
             case SDE_SCRAMBLE_NONE: po.lower.rng = RNG_SOBOL_RAW; break;
             default: throw ExprError{"unknown scramble mode"};
         }
-    } else po.lower.rng = RNG_PSEUDO;                        // anything else -> pseudo (src/sim/mod.rs:65)
+    } else if (o.generator == SDE_GEN_PHILOX) po.lower.rng = RNG_PHILOX;
+    else if (o.generator == SDE_GEN_CHACHA8) po.lower.rng = RNG_PSEUDO;   // anything else -> pseudo (src/sim/mod.rs:65)
+    else throw ExprError{"unknown generator"};
     switch (o.output) {
         case SDE_OUT_PATHS: po.lower.out = o.layout == SDE_LAYOUT_TPN ? OUT_PATHS_TPN : OUT_PATHS_NTP; break;
         case SDE_OUT_TERMINAL: po.lower.out = OUT_TERMINAL; break;

@@ -349,6 +349,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     const bool sobol = opt.rng == RNG_SOBOL_CP || opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW;
     const int KK = K > 0 ? K : 1;
     L.ch = (chacha && K > 0) ? 8 / gcd_int(8, K) : 1;
+    if (opt.rng == RNG_PHILOX && K > 0) L.ch = 4 / gcd_int(4, K);   // step groups start on a Philox block (4 draws) boundary
 
     // ---- steady-state cache position: where does one step leave the cache?
     {
@@ -396,7 +397,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     L.unr = std::max(L.ch, K <= 2 ? 4 : (K <= 4 ? 2 : 1));
     // full paths in reference order: straight from registers as aligned 256-bit stores when a group is 4 steps
     // and no ChaCha block alignment ties groups to the time origin; otherwise through the shared-memory transpose
-    const bool sector_stores_ok = opt.out == OUT_PATHS_NTP && !chacha && L.unr == 4 && P <= 8 && opt.direct != 0 && !opt.f32;
+    const bool sector_stores_ok = opt.out == OUT_PATHS_NTP && !chacha && opt.rng != RNG_PHILOX && L.unr == 4 && P <= 8 && opt.direct != 0 && !opt.f32;
     L.direct = sector_stores_ok && (L.block % 128) == 0;
     // Sobol-driven full paths whose tables fit in shared memory for the whole time grid: persistent warps, no time tiles
     {

@@ -11,7 +11,7 @@
 
 namespace sde {
 
-enum RngMode { RNG_PSEUDO = 0, RNG_SOBOL_CP = 1, RNG_SOBOL_XOR = 2, RNG_SOBOL_RAW = 3, RNG_INJECT = 4 };
+enum RngMode { RNG_PSEUDO = 0, RNG_SOBOL_CP = 1, RNG_SOBOL_XOR = 2, RNG_SOBOL_RAW = 3, RNG_INJECT = 4, RNG_PHILOX = 5 };
 enum OutMode { OUT_PATHS_NTP = 0, OUT_PATHS_TPN = 1, OUT_TERMINAL = 2, OUT_MOMENTS = 3 };
 enum SchemeId { SCHEME_EULER = 0, SCHEME_RK = 1 };
 

@@ -20,6 +20,13 @@ typedef unsigned int sde_u32;
 typedef unsigned long long sde_u64;
 #endif
 
+#ifndef SDE_ICDF_F32SEED
+#define SDE_ICDF_F32SEED 1                      /* FAST map: 1 = FP32-unit seeds + quadratic steps (sde_icdf_as_tail_f32seed), 0 = MUFU.*64H seeds + cubic steps */
+#endif
+#ifndef SDE_ICDF_HORNER
+#define SDE_ICDF_HORNER 1                       /* FP32-seed variant: N(t), D(t) by Horner in t (0: the even/odd split in w = t^2) */
+#endif
+
 #define SDE_AS_C0 2.515517
 #define SDE_AS_C1 0.802853
 #define SDE_AS_C2 0.010328
@@ -70,23 +77,19 @@ __device__ __forceinline__ double sde_rcp_approx(double a) {
 #else
 #define SDE_ICDF_Y_OFFSET_K32 45.74771391695639    /* 66 ln 2: w = 1.m 2^(pos-33) */
 #endif
+// With SDE_ICDF_F32SEED the map works on 16 x (-2 ln w) (sde_icdf_as_tail_f32seed): both tables are stored times 16 (exact).
 __device__ __forceinline__ void sde_icdf_table_load(double* s_table, int tid, int nthreads, double y_offset = 0.0) {
+    const double sc = SDE_ICDF_F32SEED ? 16.0 : 1.0;
     for (int i = tid; i < 128 * SDE_ICDF_TABLE_REPL; i += nthreads) {
         const int idx = i / SDE_ICDF_TABLE_REPL;
         s_table[2 * i] = sde_icdf_log_table[idx][0];
-        s_table[2 * i + 1] = sde_icdf_log_table[idx][1] + y_offset;
+        s_table[2 * i + 1] = (sde_icdf_log_table[idx][1] + y_offset) * sc;
     }
-    for (int h = tid; h < 64; h += nthreads) s_table[SDE_ICDF_LOG_DOUBLES + h] = (double)(h - 53) * -1.3862943611198906;
+    for (int h = tid; h < 64; h += nthreads) s_table[SDE_ICDF_LOG_DOUBLES + h] = (double)(h - 53) * -1.3862943611198906 * sc;
 }
 
 // Constants of the FAST path live in constant memory so that FP64 instructions read them as
 // c[bank][offset] operands instead of spending issue slots on 64-bit immediate moves.
-#ifndef SDE_ICDF_HORNER
-#define SDE_ICDF_HORNER 1                       /* FP32-seed variant: N(t), D(t) by Horner in t (0: the even/odd split in w = t^2) */
-#endif
-#ifndef SDE_ICDF_F32SEED
-#define SDE_ICDF_F32SEED 1                      /* wide-table map: 1 = FP32-unit seeds + quadratic steps (see below), 0 = MUFU.*64H seeds + cubic steps */
-#endif
 __constant__ double sde_kc[24] = {
     0x1.0000999a03338p-1,   // 0  a3  } degree-3 minimax polynomial for -2 log1p(r) / r on |r| <= 2^-8,
     -0x1.55560888fbbc1p-1,  // 1  a2  } a1 = 1, a0 = -2 exact  (max |err| 4.9e-14 absolute in -2 ln w)
@@ -101,7 +104,8 @@ __constant__ double sde_kc[24] = {
     -0.6666666666666666 * 16.0,            // 14  16 x (-2/3)
     SDE_AS_C0 * 16.0, SDE_AS_C1 * 16.0,    // 15, 16
     SDE_AS_D1 * 16.0,                      // 17
-    SDE_AS_C2 * 16.0, SDE_AS_D3 * 16.0, SDE_AS_D2 * 16.0};   // 18, 19, 20
+    SDE_AS_C2 * 16.0, SDE_AS_D3 * 16.0, SDE_AS_D2 * 16.0,    // 18, 19, 20
+    0x1.0000999a03338p-1 * 16.0, -0x1.55560888fbbc1p-1 * 16.0};   // 21, 22: a3, a2 times 16
 // SDE_KC(i): coefficient i of the FAST path.
 //   SDE_KC_MODE 0  the __constant__ array above (ptxas hoists the loads into vector registers)
 //   SDE_KC_MODE 1  literals (same)
@@ -138,6 +142,8 @@ __constant__ double sde_kc[24] = {
 #define SDE_KCL_18 (SDE_AS_C2 * 16.0)
 #define SDE_KCL_19 (SDE_AS_D3 * 16.0)
 #define SDE_KCL_20 (SDE_AS_D2 * 16.0)
+#define SDE_KCL_21 (0x1.0000999a03338p-1 * 16.0)
+#define SDE_KCL_22 (-0x1.55560888fbbc1p-1 * 16.0)
 #define SDE_KC(i) SDE_KCL_##i
 #if SDE_KC_MODE == 2
 // SDE_KU(i): a coefficient that is the ONLY non-register operand of its instruction (a DFMA takes one uniform-register,
@@ -183,12 +189,21 @@ __device__ __forceinline__ double sde_seed_junk_low(double seed) {
 // everything after the logarithm: w2 = -2 ln w  in [1.386, 73.5]  ->  x = t - N(t)/D(t), t = sqrt(w2).
 // `d1`, `d2` are dead values whose low words seed the MUFU results (see SDE_SEED_LOW).
 __device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double d1, const double d2);
+__device__ __forceinline__ double sde_icdf_as_tail_f32seed(const double w16);
+// `base` = e (-2 ln 2) - 2 ln c from the tables of sde_icdf_table_load (times 16 with SDE_ICDF_F32SEED)
 __device__ __forceinline__ double sde_icdf_as_core_b(const double m, const double2 tc, const double base) {
     const double r = fma(m, tc.x, -1.0);
+#if SDE_ICDF_F32SEED
+    double q = fma(r, SDE_KC(21), SDE_KC(22));               // 16 x the degree-3 minimax polynomial of -2 log1p(r) / r
+    q = fma(q, r, 16.0);
+    q = fma(q, r, -32.0);
+    return sde_icdf_as_tail_f32seed(fma(q, r, base));
+#else
     double q = fma(r, SDE_KC(0), SDE_KC(1));
     q = fma(q, r, 1.0);
     q = fma(q, r, -2.0);
     return sde_icdf_as_tail(fma(q, r, base), tc.x, base);
+#endif
 }
 __device__ __forceinline__ double sde_icdf_as_tail(const double w2, const double d1, const double d2) {
     // t = sqrt(w2): y0 ~ w2^-1/2, g = w2 y0, e2 = 1 - w2 y0^2, t = g (1 + e2/2 + 3/8 e2^2)
@@ -305,7 +320,9 @@ __device__ __forceinline__ double sde_icdf_fast_j32s(sde_u32 j, sde_u32 neg, sde
     // The int -> f64 conversion runs on the XU pipe (like FLO and the MUFU seeds), which has room; the variant
     // SDE_ICDF_EXP_MAGIC builds D = 32 + pos/2 with an integer multiply-add on the high word instead (two integer
     // instructions: the multiply-add and a zero low word).
-#if SDE_ICDF_EXP_MAGIC
+#if SDE_ICDF_F32SEED
+    const double base = fma((double)pos, SDE_KU(13), tc.y);  // the table is loaded times 16 (sde_icdf_table_load)
+#elif SDE_ICDF_EXP_MAGIC
     sde_u32 dh;
     asm("mad.lo.u32 %0, %1, 16384, 0x40400000;" : "=r"(dh) : "r"((sde_u32)pos));
     const double base = fma(__hiloint2double((int)dh, 0), SDE_KC(9), tc.y);

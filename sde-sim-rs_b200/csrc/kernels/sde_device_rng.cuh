@@ -74,6 +74,34 @@ struct SdeChaCha8Stream {
     }
 };
 
+// ---------------------------------------------------------------- Philox4x32-10 -------
+// Counter-based generator of the generator = "philox" tier (Salmon et al., SC'11; Random123 / cuRAND Philox4_32_10): not in the
+// reference — north_star asks the timed pseudo-random MC path only for STATISTICAL agreement with src/rng/pseudo.rs, and
+// ChaCha8's 8 rounds over 16 words cost ~48 integer instructions per f64 draw on the half-rate ALU pipe (the bound of the
+// terminal-only configs, profiles/r1_terminal_pipes.md).  One block = 4 32-bit draws, ~17 instructions per draw.
+//   key = the two words of the seed; counter = (lo32(scenario), hi32(scenario), block, 0); draw #i of a path = word i & 3 of
+//   block i >> 2; uniform = (word + 1/2) 2^-32 — the same 32-bit form as the digital-shift Sobol uniforms, so the integer
+//   front end of the inverse normal applies unchanged.
+__device__ __forceinline__ void sde_philox4x32_10(sde_u32 c0, sde_u32 c1, sde_u32 c2, sde_u32 c3, sde_u32 k0, sde_u32 k1, sde_u32 (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const sde_u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const sde_u32 h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct SdePhiloxStream {
+    sde_u32 k0, k1, s0, s1;
+    sde_u32 buf[4];
+    sde_u32 block;
+    __device__ __forceinline__ void init(sde_u64 seed, sde_u64 scenario) {
+        k0 = (sde_u32)seed; k1 = (sde_u32)(seed >> 32); s0 = (sde_u32)scenario; s1 = (sde_u32)(scenario >> 32); block = 0;
+    }
+    __device__ __forceinline__ void refill() { sde_philox4x32_10(s0, s1, block, 0u, k0, k1, buf); ++block; }
+};
+
 // ---------------------------------------------------------------- Sobol ---------------
 // Direction numbers are stored as the top 32 bits of the 64-bit integers: exact for point
 // indices n < 2^32 (such points only touch direction numbers 1..32, whose low 32 bits are 0).

@@ -32,6 +32,7 @@
 //   SDE_P, SDE_K, SDE_KK           processes / stochastic factors / max(K, 1)
 //   SDE_RNG                        0 pseudo(ChaCha8)  1 sobol+per-path CP shift (reference)
 //                                  2 sobol+XOR digital shift  3 sobol raw  4 injected draws
+//                                  5 Philox4x32-10 (generator = "philox": counter-based MC tier, not in the reference)
 //   SDE_OUT                        0 paths [N][T][P]  1 paths [T][P][N]  2 terminal [N][P]  3 moments
 //   SDE_ICDF                       0 reference  1 fast  2 single (FP32 evaluation)
 //   SDE_NEEDS_U0                   1 when the scheme consumes u[t][0] directly (Runge–Kutta sk)
@@ -51,6 +52,7 @@
 #define SDE_NW (SDE_BLOCK / 32)
 #define SDE_USES_CHACHA (SDE_RNG == 0 || SDE_RNG == 1)
 #define SDE_USES_SOBOL (SDE_RNG == 1 || SDE_RNG == 2 || SDE_RNG == 3)
+#define SDE_USES_PHILOX (SDE_RNG == 5)
 #ifndef SDE_KK
 #define SDE_KK (SDE_K > 0 ? SDE_K : 1)
 #endif
@@ -235,6 +237,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     SdeChaCha8Stream cha;
     cha.init(prm.seed + s_global);                                 // sim/mod.rs:56,65 (wrapping add)
 #endif
+#if SDE_USES_PHILOX
+    SdePhiloxStream phx;
+    phx.init(prm.seed, s_global);
+#endif
     sde_u32 rare_min = 0xffffffffu;                                // see draw_fixup
     (void)rare_min;
 
@@ -297,7 +303,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #else
             // wide models: a partially unrolled loop keeps 4 inverse-normal chains in flight and lets the draws live in a
             // (L1-resident) local array instead of 2 K registers; ChaCha modes index their block buffer statically
-#if SDE_K >= 16 && !SDE_USES_CHACHA
+#if SDE_K >= 16 && !SDE_USES_CHACHA && !SDE_USES_PHILOX
 #pragma unroll 4
 #else
 #pragma unroll
@@ -311,6 +317,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #if SDE_USES_SOBOL
                 const int dl = tl * SDE_K + k;
                 const sde_u32 x = s_bw[dl * SDE_NW + warp] ^ s_lane[dl * 32 + lane];    // (digitally shifted) Sobol integer
+#endif
+#if SDE_USES_PHILOX
+                const int pslot = (j * SDE_K + k) & 3;     // compile-time after unrolling: groups start on a block boundary
+                if (pslot == 0) phx.refill();
+                const sde_u32 x = phx.buf[pslot];          // u = (x + 1/2) 2^-32
 #endif
 #if SDE_RNG == 0
                 // uniforms of the form j * 2^-53 stay in the integer pipe until the draw is needed
@@ -330,8 +341,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 } else {
                     zu[k] = (double)(long long)jc * 1.1102230246251565e-16;
                 }
-#elif SDE_RNG == 2
-                // digital shift: u = ((x ^ mask) + 1/2) * 2^-32, one 32-bit mask per dimension (already folded into x)
+#elif SDE_RNG == 2 || SDE_RNG == 5
+                // digital shift: u = ((x ^ mask) + 1/2) * 2^-32, one 32-bit mask per dimension (already folded into x);
+                // Philox words take the same 32-bit form
                 if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1

@@ -38,6 +38,7 @@ _DTYPES = {"f64": DTYPE_F64, "float64": DTYPE_F64, "f32": DTYPE_F32, "float32": 
 _ICDFS = {"reference": ICDF_REFERENCE, "fast": ICDF_FAST, "single": ICDF_SINGLE}
 _ARITHS = {"strict": ARITH_STRICT, "fast": ARITH_FAST}
 _RKS = {"reference": RK_REFERENCE, "textbook": RK_TEXTBOOK}
+_GENERATORS = {"chacha8": _ffi.GEN_CHACHA8, "philox": _ffi.GEN_PHILOX}
 
 
 def version() -> str:
@@ -87,7 +88,7 @@ def parse_equations(processes_equations: Sequence[str], time_steps: Sequence[flo
 
 def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, layout: str, scramble: str, icdf: str,
                   arithmetic: str, rk_variant: str, inject_ptr: int = 0, tile_steps: int = 0, block_threads: int = 0,
-                  min_blocks: int = 0, ntp_direct: int = 0, dtype: str = "f64", wide_mma: int = 0):
+                  min_blocks: int = 0, ntp_direct: int = 0, dtype: str = "f64", wide_mma: int = 0, generator: str = "chacha8"):
     o = _ffi.default_options()
     o.device = device
     o.seed = seed & (2**64 - 1)
@@ -105,6 +106,7 @@ def _make_options(*, device: int, seed: int, scenario_offset: int, output: str, 
     o.ntp_direct = ntp_direct
     o.dtype = _pick(_DTYPES, dtype, "dtype")
     o.wide_mma = wide_mma
+    o.generator = _pick(_GENERATORS, generator, "generator")
     return o
 
 
@@ -121,7 +123,7 @@ class Plan:
                  layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
                  arithmetic: str = "strict", rk_variant: str = "reference", device: Optional[int] = None,
                  inject=None, tile_steps: int = 0, block_threads: int = 0, min_blocks: int = 0, ntp_direct: int = 0,
-                 dtype: str = "f64", wide_mma: int = 0):
+                 dtype: str = "f64", wide_mma: int = 0, generator: str = "chacha8"):
         self.universe = universe
         self.dtype = "f32" if _pick(_DTYPES, dtype, "dtype") == DTYPE_F32 else "f64"
         self.scheme, self.rng_method = scheme, rng_method
@@ -132,7 +134,7 @@ class Plan:
                              scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant,
                              inject_ptr=(inject.data_ptr() if inject is not None else 0), tile_steps=tile_steps,
                              block_threads=block_threads, min_blocks=min_blocks, ntp_direct=ntp_direct, dtype=dtype,
-                             wide_mma=wide_mma)
+                             wide_mma=wide_mma, generator=generator)
         h = C.c_void_p()
         rc = _ffi.lib().sde_plan_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), C.byref(h))
         _ffi.check(rc, prefix_runtime="Simulation failed: ")
@@ -308,7 +310,7 @@ def _cached_plan(equations, time_steps, scheme, rng_method, **kw) -> Plan:
     return plan
 
 
-_EXTENSIONS = ("seed", "output", "layout", "scramble", "icdf", "arithmetic", "rk_variant", "device", "scenario_offset", "dtype")
+_EXTENSIONS = ("seed", "output", "layout", "scramble", "icdf", "arithmetic", "rk_variant", "device", "scenario_offset", "dtype", "generator")
 
 
 def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
@@ -324,7 +326,8 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
     this when seed is None), `output` paths|terminal|moments, `layout`, `scramble` cp_shift_per_path (reference
     behaviour) | xor | none, `icdf` reference|fast|single, `arithmetic` strict|fast, `rk_variant` reference|textbook,
     `device`, `scenario_offset`, `dtype` f64|f32 (f32: state, arithmetic and stored values in single precision; needs
-    arithmetic="fast").  With any of them the result is a `Filtration` (the dense value tensor, resident on the GPU) unless
+    arithmetic="fast"), `generator` chacha8 (the reference's stream, bit-exact) | philox (Philox4x32-10: a cheaper
+    counter-based stream for rng_method != "sobol"; agrees with the reference statistically, not draw for draw).  With any of them the result is a `Filtration` (the dense value tensor, resident on the GPU) unless
     frame=True; frame=False always returns the `Filtration`.
     """
     unknown = [k for k in ext if k not in _EXTENSIONS]
@@ -349,7 +352,7 @@ def _simulate_filtration(processes_equations: Sequence[str], time_steps: Sequenc
                          seed: Optional[int] = None, output: str = "paths", layout: str = "NTP",
                          scramble: str = "cp_shift_per_path", icdf: str = "reference", arithmetic: str = "strict",
                          rk_variant: str = "reference", device: Optional[int] = None, scenario_offset: int = 0,
-                         dtype: str = "f64") -> Filtration:
+                         dtype: str = "f64", generator: str = "chacha8") -> Filtration:
     if not isinstance(scenarios, (int, np.integer)) or scenarios <= 0:
         raise ValueError("scenarios must be a positive integer")                      # py_binding.rs:20-24
     if seed is None:
@@ -357,7 +360,7 @@ def _simulate_filtration(processes_equations: Sequence[str], time_steps: Sequenc
     # parse first so that equation errors surface as ValueError before any CUDA work (py_binding.rs:30-32)
     plan = _cached_plan(list(processes_equations), time_steps, scheme, rng_method, output=output, layout=layout,
                         scramble=scramble, icdf=icdf, arithmetic=arithmetic, rk_variant=rk_variant, device=device,
-                        dtype=dtype)
+                        dtype=dtype, generator=generator)
     values = plan.run(dict(initial_values), int(scenarios), seed=seed, scenario_offset=scenario_offset)
     return Filtration(values, plan.universe.time_steps, plan.universe.process_names, output=output, layout=layout,
                       scenario_offset=scenario_offset, seed=seed)
@@ -400,7 +403,8 @@ class DevicePlans:
 
     def __init__(self, universe: Universe, scheme: str = "euler", rng_method: str = "pseudo", *, devices: Optional[Sequence[int]] = None,
                  output: str = "paths", layout: str = "NTP", scramble: str = "cp_shift_per_path", icdf: str = "reference",
-                 arithmetic: str = "strict", rk_variant: str = "reference", dtype: str = "f64", block_threads: int = 0, wide_mma: int = 0):
+                 arithmetic: str = "strict", rk_variant: str = "reference", dtype: str = "f64", block_threads: int = 0, wide_mma: int = 0,
+                 generator: str = "chacha8"):
         import torch
 
         self.universe, self.output, self.layout = universe, output, layout
@@ -409,7 +413,8 @@ class DevicePlans:
         if not devs:
             raise RuntimeError("Simulation failed: no CUDA device (there is no CPU fallback)")
         opts = _make_options(device=devs[0], seed=0, scenario_offset=0, output=output, layout=layout, scramble=scramble, icdf=icdf,
-                             arithmetic=arithmetic, rk_variant=rk_variant, dtype=dtype, block_threads=block_threads, wide_mma=wide_mma)
+                             arithmetic=arithmetic, rk_variant=rk_variant, dtype=dtype, block_threads=block_threads, wide_mma=wide_mma,
+                             generator=generator)
         h = C.c_void_p()
         arr = (C.c_int32 * len(devs))(*devs)
         rc = _ffi.lib().sde_device_plans_create(universe._h, scheme.encode(), rng_method.encode(), C.byref(opts), arr, len(devs), C.byref(h))

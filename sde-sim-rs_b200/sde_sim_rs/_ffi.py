@@ -22,6 +22,7 @@ ICDF_REFERENCE, ICDF_FAST, ICDF_SINGLE = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
 ARITH_STRICT, ARITH_FAST = 0, 1
 RK_REFERENCE, RK_TEXTBOOK = 0, 1
+GEN_CHACHA8, GEN_PHILOX = 0, 1
 
 
 class SdeOptions(C.Structure):
@@ -44,6 +45,7 @@ class SdeOptions(C.Structure):
         ("ntp_direct", C.c_int32),
         ("dtype", C.c_int32),
         ("wide_mma", C.c_int32),
+        ("generator", C.c_int32),
     ]
 
 

@@ -34,10 +34,18 @@ def test_reference_example_models(oracle, name, model, scheme, rng_method):
     ref = oracle.simulate(U, init, N, sch, rng_method, seed=11)
     got = S.simulate(eqs, times, N, init, rng_method, sch, seed=11).to_numpy()
     assert got.shape == ref.shape == (N, len(times), len(eqs))
-    ok = np.array([rel_err(got[i], ref[i]) <= 1e-12 for i in range(N)])
+    # the payoff X2 = max(X1 - 100, 0) cancels X1 against 100 (X1 starts AT 100): its error is X1's absolute error, so it is
+    # held to 1e-12 of X1's magnitude; every SDE process to 1e-12 relative
+    levy = [i for i, e in enumerate(eqs) if e.lstrip().startswith("d")]
+    payoff = [i for i in range(len(eqs)) if i not in levy]
+    scale = float(np.abs(ref[:, :, levy]).max())
+
+    def path_ok(i):
+        return rel_err(got[i][:, levy], ref[i][:, levy]) <= 1e-12 and (not payoff or float(np.abs(got[i][:, payoff] - ref[i][:, payoff]).max()) <= 1e-12 * scale)
+
+    ok = np.array([path_ok(i) for i in range(N)])
     flips = int((~ok).sum())
     assert flips <= (2 if any("dN" in e for e in eqs) else 0), (name, sch, rng_method, flips)
-    assert rel_err(got[ok], ref[ok]) <= 1e-12
     if name == "example.rs":
         # dN1(0.5 * cos(t)): a negative intensity gives no jumps (increment.rs:183), a positive one does
         assert np.isfinite(got).all()

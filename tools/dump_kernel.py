@@ -24,6 +24,8 @@ CONFIGS = {
     "c2strict": (GBM, 252, "euler", "sobol", dict(scramble="xor", icdf="reference", arithmetic="strict")),
     "c1": (GBM, 252, "euler", "pseudo", dict()),
     "c5": (GBM, 365, "euler", "pseudo", dict(output="moments", icdf="fast", arithmetic="fast")),
+    "c5p": (GBM, 365, "euler", "pseudo", dict(output="moments", icdf="fast", arithmetic="fast", generator="philox")),
+    "c2cp": (GBM, 252, "euler", "sobol", dict(icdf="fast", arithmetic="fast")),
     "c3": (HESTON, 1000, "runge-kutta", "sobol", dict(scramble="xor", icdf="fast", arithmetic="fast")),
 }
 
@@ -36,7 +38,7 @@ def main():
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant="reference",
-                        tile_steps=int(extra.get("tt", 0)), block_threads=int(extra.get("block", 0)))
+                        tile_steps=int(extra.get("tt", 0)), block_threads=int(extra.get("block", 0)), generator=kw.get("generator", "chacha8"))
     src = C.c_void_p()
     _ffi.check(_ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), 0, C.byref(src), None))
     text = C.string_at(src).decode()

@@ -335,13 +335,13 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / K
     value = sample * D / dt
     desc = f"{sample} paths x {D} steps of C2 per step (oracle C++ port of the reference algorithm, OpenMP, {cores} threads)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample": desc},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def run_gpu(args):
@@ -521,12 +521,31 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
             "timed_output_parity": parity, "plan_create_ms": plan_ms, "device_peaks": peaks, "configs": configs, "c5_strong": c5,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries write there too (NCCL prints its version banner on fd 1 at NCCL_DEBUG=WARN
+    and VERSION), so fd 1 is pointed at stderr for the whole run and the line goes to a private copy of the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

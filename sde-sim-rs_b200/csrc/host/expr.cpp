@@ -211,6 +211,36 @@ bool Expr::uses_var(int idx) const {
     return false;
 }
 
+void Expr::product_form(double& kappa, std::vector<int>& factors) const {
+    kappa = 1.0;
+    factors.clear();
+    product_walk(root_, kappa, factors);
+}
+
+void Expr::product_walk(int i, double& kappa, std::vector<int>& factors) const {
+    const ExprNode& n = nodes_[i];
+    switch (n.op) {
+        case Op::Const: kappa *= n.value; return;
+        case Op::Neg: kappa = -kappa; product_walk(n.args[0], kappa, factors); return;
+        case Op::Mul: product_walk(n.args[0], kappa, factors); product_walk(n.args[1], kappa, factors); return;
+        case Op::Div: {
+            const ExprNode& d = nodes_[n.args[1]];
+            if (d.op == Op::Const && d.value != 0.0 && std::isfinite(1.0 / d.value)) {
+                kappa /= d.value;
+                product_walk(n.args[0], kappa, factors);
+                return;
+            }
+            break;
+        }
+        case Op::Call:
+            if (n.fn == "e") { kappa *= 2.718281828459045; return; }
+            if (n.fn == "pi") { kappa *= 3.141592653589793; return; }
+            break;
+        default: break;
+    }
+    factors.push_back(i);
+}
+
 std::string Expr::emit_cuda(bool strict, const std::string& c, const std::string& t) const {
     return emit_node(root_, strict, c, t);
 }
@@ -235,7 +265,18 @@ std::string Expr::emit_node(int i, bool strict, const std::string& c, const std:
         case Op::Pow: {
             const ExprNode& ex = nodes_[n.args[1]];
             // powf(x, 0.5): equal to sqrt except for -0.0 / -inf; arithmetic=fast takes the MUFU seed + one cubic step (<= 1 ulp)
-            if (ex.op == Op::Const && ex.value == 0.5) return std::string(strict ? "sqrt(" : "sde_f_sqrt_fast(") + A(0) + ")";
+            if (ex.op == Op::Const && ex.value == 0.5) {
+                // max(x, 0)^0.5 (the full-truncation root of square-root diffusions): one fused helper under arithmetic=fast,
+                // whose range guards run on the integer pipe instead of four FP64 compares
+                const ExprNode& b = nodes_[n.args[0]];
+                if (!strict && !real_literals_f32() && b.op == Op::Call && b.fn == "max" && b.args.size() == 2) {
+                    const ExprNode& m0 = nodes_[b.args[0]];
+                    const ExprNode& m1 = nodes_[b.args[1]];
+                    const bool z0 = m0.op == Op::Const && m0.value == 0.0, z1 = m1.op == Op::Const && m1.value == 0.0;
+                    if (z0 != z1) return "sde_f_sqrt_max0_fast(" + emit_node(b.args[z0 ? 1 : 0], strict, c, t) + ")";
+                }
+                return std::string(strict ? "sqrt(" : "sde_f_sqrt_fast(") + A(0) + ")";
+            }
             if (ex.op == Op::Const && ex.value == 2.0) return "sde_f_sq(" + A(0) + ")";
             if (ex.op == Op::Const && ex.value == 1.0) return A(0);
             return "pow(" + A(0) + ", " + A(1) + ")";

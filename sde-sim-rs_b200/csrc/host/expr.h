@@ -37,6 +37,13 @@ class Expr {
     // separately rounded __dmul_rn/__dadd_rn so FMA contraction cannot move results.
     std::string emit_cuda(bool strict, const std::string& cache_name = "c", const std::string& time_name = "ct") const;
 
+    // Product form (arithmetic = fast lowering): value = kappa * prod_i node(factors[i]).  Multiplications, negations, literal
+    // factors and divisions by a literal are flattened into kappa; everything else is a factor (a node index for emit_cuda_node).
+    void product_form(double& kappa, std::vector<int>& factors) const;
+    std::string emit_cuda_node(int node, bool strict, const std::string& cache_name = "c", const std::string& time_name = "ct") const {
+        return emit_node(node, strict, cache_name, time_name);
+    }
+
     bool is_constant() const;
     const std::string& source() const { return src_; }
     const std::vector<ExprNode>& nodes() const { return nodes_; }
@@ -49,6 +56,7 @@ class Expr {
     int root_ = -1;
     friend class ExprParserImpl;
     std::string emit_node(int i, bool strict, const std::string& c, const std::string& t) const;
+    void product_walk(int i, double& kappa, std::vector<int>& factors) const;
 };
 
 std::string format_double(double v);   // shortest round-trip literal usable in CUDA source

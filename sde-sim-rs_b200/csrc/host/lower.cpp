@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <numeric>
+#include <map>
 #include <sstream>
 
 namespace sde {
@@ -27,6 +28,11 @@ class StepGen {
     // the same constants evaluated on the host, [slot][step] (IEEE fma / multiply / sqrt: bit-identical to the device),
     // so that constants which do not change along the time grid can be emitted as literals instead of table reads
     std::vector<std::vector<double>> slot_values;
+    // spread along the time grid (max - min) below which a slot counts as constant under arithmetic=fast: what re-rounding
+    // the time points by a few ulp would do to it.  A uniform grid k/D has dt values that differ by ~ulp(t_end) only because
+    // k/D is not representable; the factor 4 covers both end points of a step and the subtraction.
+    std::vector<double> slot_tol;
+    std::vector<bool> slot_mult;                             // the slot is a multiplier of an FMA (kept on the uniform datapath when constant)
     std::vector<double> model_consts;                        // literal coefficients placed in __constant__ memory (sde_mc[])
     bool matrix = false;                                     // the step was emitted in matrix form (wide linear model)
     std::vector<double> mat_drift, mat_M;                    // matrix form: a_i [NB*8] and loadings M [NB][K][8]
@@ -40,6 +46,10 @@ class StepGen {
         o_ = &o;
         slots.clear();
         slot_values.clear();
+        slot_mult.clear();
+        slot_tol.clear();
+        factor_tmp_.clear();
+        factor_tmp_id_ = 0;
         model_consts.clear();
         pre_.str("");
         w_declared_.assign(u_.K(), false);
@@ -55,6 +65,13 @@ class StepGen {
                     n += 1;
                     for (bool b : used) n += b ? 1 : 0;
                 }
+            // the factored form of the other processes (arithmetic=fast): one constant per (group, increment kind)
+            if (!opt_.strict)
+                for (int p : u_.levy_indices) {
+                    const Process& pr = u_.processes[p];
+                    if (opt_.scheme == SCHEME_EULER && linear_in_own_state(pr, p, lin)) continue;
+                    n += factorise(pr).slots_needed(opt_.scheme == SCHEME_RK);
+                }
             hoist_ = n <= 16;
         }
         const int P = u_.P();
@@ -62,7 +79,7 @@ class StepGen {
         matrix = matrix_form_ok();
         if (matrix) { emit_matrix_form(); return state_; }
         for (int p = 0; p < P; ++p) line("sde_real n" + std::to_string(p) + " = " + format_real(0.0) + ";");   // row t+1 is zero until set (filtration.rs:28)
-        if (opt_.scheme == SCHEME_EULER) euler(); else runge_kutta();
+        if (opt_.scheme == SCHEME_EULER) euler(); else if (!opt_.strict) runge_kutta_fast(); else runge_kutta();
         for (int p = 0; p < P; ++p) line("row[" + std::to_string(p) + "] = n" + std::to_string(p) + ";");
         return state_;
     }
@@ -72,6 +89,15 @@ class StepGen {
     const LowerOptions& opt_;
     CacheAt state_ = OLD;
     std::ostringstream* o_ = nullptr;
+    // |d slot| for a re-rounding of the time points: slot = kappa * dt or kappa * sqrt(dt)
+    double grid_tol(double kappa, bool sqrt_of_dt) const {
+        double tmax = 0.0, dtmin = INFINITY;
+        for (double t : u_.times) tmax = std::max(tmax, std::fabs(t));
+        for (size_t q = 0; q + 1 < u_.times.size(); ++q) dtmin = std::min(dtmin, u_.times[q + 1] - u_.times[q]);
+        const double d = 4.0 * (std::nextafter(tmax, INFINITY) - tmax);
+        if (!(dtmin > 0.0) || !std::isfinite(d)) return 0.0;
+        return std::fabs(kappa) * (sqrt_of_dt ? d / (2.0 * std::sqrt(dtmin)) : d);
+    }
     std::ostringstream pre_;
     std::ostringstream matrix_decl_;
     std::vector<bool> w_declared_;
@@ -93,6 +119,7 @@ class StepGen {
         }
         line(std::string("ct = ") + (at == CUR ? "t_cur;" : "t_next;"));
         state_ = at;
+        factor_tmp_.clear();
     }
     // Function::eval (func.rs:32-42)
     std::string eval(const Expr& e, CacheAt at) {
@@ -190,6 +217,200 @@ class StepGen {
         state_ = CUR;                                        // as after the refresh of the term-by-term form
     }
 
+    // ---- arithmetic = fast: coefficients in product form, terms grouped by their state-dependent part ----------------------
+    // A Levy process is  dX = sum_j C_j(X, t) dx_j.  Each C_j is flattened to kappa_j * prod(factors) (Expr::product_form).
+    // Terms with the same factor product V_g form a group:  sum_j C_j dx_j = sum_g V_g * W_g,  W_g = sum_{j in g} kappa_j dx_j.
+    // W_g does not depend on the state, so both Runge-Kutta stages share it, and kappa_j dt / kappa_j sqrt(dt) are per-step
+    // constants (slots).  Factors common to all groups of a process are taken out of the sum:  F * sum_g (V_g / F) W_g.
+    // Heston's dS = 0.05 S dt + sqrt(v+) S dW becomes S * fma(sqrt(v+), b z, a): 2 FP64 instructions per stage instead of 5.
+    // Every regrouping moves a result by <= 1 ulp of its largest term (the mode's stated <= ~3 ulp per step).
+    struct Group {
+        std::vector<std::string> f, rest;                    // factor strings (sorted); f minus the process's common factors
+        std::vector<size_t> terms;
+        bool has_dt = false, has_wiener = false;
+        int n_wiener_factors = 0;
+    };
+    struct Factored {
+        std::vector<Group> groups;
+        std::vector<std::string> common;
+        std::vector<double> kappa;                           // per term
+        size_t slots_needed(bool rk) const {
+            size_t n = 0;
+            for (const Group& g : groups) n += (g.has_dt ? 1 : 0) + (size_t)g.n_wiener_factors + ((rk && g.has_wiener) ? 1 : 0);
+            return n;
+        }
+    };
+    Factored factorise(const Process& pr) const {
+        Factored F;
+        F.kappa.resize(pr.terms.size());
+        for (size_t j = 0; j < pr.terms.size(); ++j) {
+            std::vector<int> nodes;
+            pr.terms[j].coeff.product_form(F.kappa[j], nodes);
+            std::vector<std::string> f;
+            for (int nd : nodes) f.push_back(pr.terms[j].coeff.emit_cuda_node(nd, false));
+            std::sort(f.begin(), f.end());
+            Group* g = nullptr;
+            for (Group& q : F.groups) if (q.f == f) g = &q;
+            if (!g) { F.groups.emplace_back(); g = &F.groups.back(); g->f = f; }
+            g->terms.push_back(j);
+        }
+        for (Group& g : F.groups) {
+            std::vector<bool> used(u_.K(), false);
+            for (size_t j : g.terms) {
+                const Term& t = pr.terms[j];
+                if (t.kind == IncKind::Time) g.has_dt = true;
+                if (t.kind == IncKind::Wiener) { g.has_wiener = true; used[t.factor] = true; }
+            }
+            for (bool b : used) g.n_wiener_factors += b ? 1 : 0;
+        }
+        if (!F.groups.empty()) {                              // multiset intersection of the groups' factors
+            F.common = F.groups[0].f;
+            for (size_t q = 1; q < F.groups.size(); ++q) {
+                std::vector<std::string> keep, pool = F.groups[q].f;
+                for (const std::string& x : F.common) {
+                    auto it = std::find(pool.begin(), pool.end(), x);
+                    if (it != pool.end()) { keep.push_back(x); pool.erase(it); }
+                }
+                F.common = keep;
+            }
+            for (Group& g : F.groups) {
+                g.rest = g.f;
+                for (const std::string& x : F.common) g.rest.erase(std::find(g.rest.begin(), g.rest.end(), x));
+            }
+        }
+        return F;
+    }
+    // A factor that is more than a plain state read is evaluated once per cache state and named (the same root or
+    // payoff-like sub-expression usually sits in several terms and processes; ptxas does not merge the copies' selects).
+    std::map<std::string, std::string> factor_tmp_;
+    int factor_tmp_id_ = 0;
+    std::string fx(const std::string& f) {
+        if (f == "ct" || (f.size() >= 4 && f.compare(0, 2, "c[") == 0 && f.find(']') == f.size() - 1)) return f;
+        auto it = factor_tmp_.find(f);
+        if (it != factor_tmp_.end()) return it->second;
+        const std::string name = "q" + std::to_string(factor_tmp_id_++);
+        line("const sde_real " + name + " = " + f + ";");
+        factor_tmp_[f] = name;
+        return name;
+    }
+    std::string product(const std::vector<std::string>& f) {
+        std::string acc;
+        for (const std::string& x : f) { const std::string v = fx(x); acc = acc.empty() ? v : "(" + acc + " * " + v + ")"; }
+        return acc;
+    }
+    // a per-step constant kappa * dt or kappa * sqrt(dt): table slot / literal when hoisted, else computed in place
+    std::string step_const(double kappa, bool sqrt_of_dt) {
+        const std::string expr = "(" + format_real(kappa) + (sqrt_of_dt ? " * sqrt_dt)" : " * dt)");
+        if (!hoist_) return expr;
+        const int S = u_.T() - 1;
+        std::vector<double> v(S);
+        for (int q = 0; q < S; ++q) { const double dt = u_.times[q + 1] - u_.times[q]; v[q] = kappa * (sqrt_of_dt ? std::sqrt(dt) : dt); }
+        slots.push_back(expr);
+        slot_values.push_back(v);
+        slot_mult.push_back(true);
+        slot_tol.push_back(grid_tol(kappa, sqrt_of_dt));
+        return "SDE_SLOT_" + std::to_string(slots.size() - 1);
+    }
+    // W_g of every group (declared as w<p>_<g>), and for Runge-Kutta the probe weights pw<p>_<g> = (sum kappa_j) sk sqrt(dt)
+    // of the groups that hold Wiener terms.  `inc_name(j)` names the sampled increment of a Poisson term.
+    template <class IncName>
+    void emit_weights(int p, const Process& pr, const Factored& F, bool rk, IncName inc_name) {
+        for (size_t gi = 0; gi < F.groups.size(); ++gi) {
+            const Group& g = F.groups[gi];
+            double kdt = 0.0, ksum = 0.0;
+            std::vector<double> kw(u_.K(), 0.0);
+            std::vector<bool> used(u_.K(), false);
+            for (size_t j : g.terms) {
+                const Term& t = pr.terms[j];
+                if (t.kind == IncKind::Time) kdt += F.kappa[j];
+                if (t.kind == IncKind::Wiener) { kw[t.factor] += F.kappa[j]; used[t.factor] = true; ksum += F.kappa[j]; }
+            }
+            std::string acc = g.has_dt ? step_const(kdt, false) : "";
+            for (int k = 0; k < u_.K(); ++k) {
+                if (!used[k]) continue;
+                const std::string b = step_const(kw[k], true), z = "zu[" + std::to_string(k) + "]";
+                acc = acc.empty() ? "(" + b + " * " + z + ")" : "fma(" + b + ", " + z + ", " + acc + ")";
+            }
+            for (size_t j : g.terms) {
+                if (pr.terms[j].kind != IncKind::Poisson) continue;
+                const std::string kq = format_real(F.kappa[j]), x = inc_name(j);
+                acc = acc.empty() ? "(" + kq + " * " + x + ")" : "fma(" + kq + ", " + x + ", " + acc + ")";
+            }
+            const std::string id = std::to_string(p) + "_" + std::to_string(gi);
+            line("const sde_real w" + id + " = " + acc + ";");
+            if (rk && g.has_wiener) line("const sde_real pw" + id + " = sde_f_xorsign((sde_real)" + step_const(ksum, true) + ", skm);");
+        }
+    }
+    // sum_g (V_g / F) * weight_g over the groups that have the weight (fma chain onto the factor-free group)
+    std::string inner_sum(int p, const Factored& F, const char* weight, bool wiener_only) {
+        std::string acc;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t gi = 0; gi < F.groups.size(); ++gi) {
+                const Group& g = F.groups[gi];
+                if ((wiener_only && !g.has_wiener) || (pass == 0) != g.rest.empty()) continue;
+                const std::string w = weight + std::to_string(p) + "_" + std::to_string(gi);
+                if (g.rest.empty()) acc = acc.empty() ? w : "(" + acc + " + " + w + ")";
+                else { const std::string v = product(g.rest); acc = acc.empty() ? "(" + v + " * " + w + ")" : "fma(" + v + ", " + w + ", " + acc + ")"; }
+            }
+        return acc;
+    }
+    void ensure(CacheAt at) { if (state_ != at) refresh(at); }
+
+    void runge_kutta_fast() {                                // runge_kutta.rs:5-107 in the factored form above
+        const int P = u_.P();
+        // sk = +1 where u0 > 1/2 else -1 (runge_kutta.rs:18-22), kept as a sign mask
+        if (opt_.u0_bits) line("const unsigned int skm = (~u0) & 0x80000000u;   // runge_kutta.rs:18-22: sk = -1 unless u0 > 1/2 (top bit of the word)");
+        else line("const unsigned int skm = (u0 > " + format_real(0.5) + ") ? 0u : 0x80000000u;   // runge_kutta.rs:18-22: sk = -1 unless u0 > 1/2");
+        if (opt_.rk_textbook) state_ = OLD;
+        std::vector<Factored> F(P);
+        for (int p = 0; p < P; ++p) {                        // :26-35 pre-sample (Poisson intensities are evaluated here)
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            F[p] = factorise(pr);
+            for (size_t j = 0; j < pr.terms.size(); ++j) {
+                if (pr.terms[j].kind != IncKind::Poisson) continue;
+                std::string x = increment(pr.terms[j]);
+                line("const sde_real inc_" + std::to_string(p) + "_" + std::to_string(j) + " = " + x + ";");
+            }
+            emit_weights(p, pr, F[p], true, [&](size_t j) { return "inc_" + std::to_string(p) + "_" + std::to_string(j); });
+        }
+        for (int p = 0; p < P; ++p) line("const sde_real x" + std::to_string(p) + " = row[" + std::to_string(p) + "];");   // :38-42
+        auto stage = [&](int p, const char* tag, CacheAt at) {   // k = F * i  (declares f<tag>_p, i<tag>_p, k<tag>_p)
+            const Process& pr = u_.processes[p];
+            const std::string sp = std::to_string(p), t = tag;
+            if (!pr.terms.empty()) ensure(at);
+            const std::string in = inner_sum(p, F[p], "w", false);
+            line("const sde_real i" + t + "_" + sp + " = " + (in.empty() ? format_real(0.0) : in) + ";");
+            if (!F[p].common.empty()) {
+                const std::string f = product(F[p].common);
+                line("const sde_real f" + t + "_" + sp + " = " + f + ";");
+                line("const sde_real k" + t + "_" + sp + " = (f" + t + "_" + sp + " * i" + t + "_" + sp + ");");
+            } else {
+                line("const sde_real k" + t + "_" + sp + " = i" + t + "_" + sp + ";");
+            }
+        };
+        for (int p = 0; p < P; ++p) if (u_.processes[p].levy) stage(p, "1", CUR);      // :45-55  k1
+        for (int p = 0; p < P; ++p) {                        // :62-78  probe row: x + k1 + sum_j C_j sk sqrt(dt)
+            const Process& pr = u_.processes[p];
+            if (!pr.levy) continue;
+            const std::string sp = std::to_string(p);
+            const std::string pert = inner_sum(p, F[p], "pw", true);
+            if (pert.empty()) line("n" + sp + " = (x" + sp + " + k1_" + sp + ");");
+            else if (!F[p].common.empty()) line("n" + sp + " = fma(f1_" + sp + ", (i1_" + sp + " + " + pert + "), x" + sp + ");");
+            else line("n" + sp + " = ((x" + sp + " + k1_" + sp + ") + " + pert + ");");
+        }
+        for (int p = 0; p < P; ++p) if (u_.processes[p].levy) stage(p, "2", NEXT);     // :81-91  k2 at the probe row
+        for (int p : u_.levy_indices) {                      // :94-97
+            std::string sp = std::to_string(p);
+            line("n" + sp + " = fma(" + format_real(0.5) + ", (k1_" + sp + " + k2_" + sp + "), x" + sp + ");");
+        }
+        if (opt_.rk_textbook && !u_.algebraic_indices.empty()) state_ = OLD;
+        for (int a : u_.algebraic_indices) {                 // :101-106 (sees the probe row: cache not refreshed)
+            std::string ex = eval(u_.processes[a].algebraic, NEXT);
+            line("n" + std::to_string(a) + " = " + ex + ";   // algebraic '" + u_.processes[a].name + "'");
+        }
+    }
+
     void euler() {                                           // src/sim/euler.rs:5-37
         for (int p : u_.levy_indices) {
             const Process& pr = u_.processes[p];
@@ -219,6 +440,12 @@ class StepGen {
                 if (hoist_) {
                     slots.push_back(A);
                     slot_values.push_back(Av);
+                    slot_mult.push_back(false);              // the addend the factor terms accumulate onto
+                    {
+                        double asum = 0.0;
+                        for (size_t j = 0; j < pr.terms.size(); ++j) if (pr.terms[j].kind == IncKind::Time) asum += std::fabs(lin[j]);
+                        slot_tol.push_back(grid_tol(asum, false));
+                    }
                     line("sde_real g = SDE_SLOT_" + std::to_string(slots.size() - 1) + ";");
                     for (int k = 0; k < u_.K(); ++k) {
                         if (!bused[k]) continue;
@@ -226,6 +453,8 @@ class StepGen {
                         std::vector<double> Bv(S);
                         for (int q = 0; q < S; ++q) Bv[q] = bsum[k] * sqv[q];
                         slot_values.push_back(Bv);
+                        slot_mult.push_back(true);
+                        slot_tol.push_back(grid_tol(bsum[k], true));
                         line("g = fma(SDE_SLOT_" + std::to_string(slots.size() - 1) + ", zu[" + std::to_string(k) + "], g);");
                     }
                 } else {
@@ -247,6 +476,20 @@ class StepGen {
                     line("g = fma(" + format_real(lin[j]) + ", " + x + ", g);");
                 }
                 line("n" + sp + " = row[" + sp + "] * g; }");   // Levy slots of the cache always equal row t in Euler
+                continue;
+            }
+            if (!opt_.strict) {                              // factored form (see factorise)
+                if (!pr.terms.empty()) ensure(CUR);
+                factor_tmp_.clear();                         // temporaries live in this process's block
+                const Factored F = factorise(pr);
+                std::vector<std::string> incs(pr.terms.size());
+                for (size_t j = 0; j < pr.terms.size(); ++j) if (pr.terms[j].kind == IncKind::Poisson) incs[j] = increment(pr.terms[j]);
+                emit_weights(p, pr, F, false, [&](size_t j) { return incs[j]; });
+                const std::string in = inner_sum(p, F, "w", false);
+                if (in.empty()) line("n" + sp + " = row[" + sp + "]; }");
+                else if (!F.common.empty()) { const std::string f = product(F.common); line("n" + sp + " = fma(" + f + ", " + in + ", row[" + sp + "]); }"); }
+                else line("n" + sp + " = (row[" + sp + "] + " + in + "); }");
+                factor_tmp_.clear();
                 continue;
             }
             line("sde_real val = row[" + sp + "];");
@@ -335,7 +578,10 @@ struct RealLiteralMode {                                     // format_real() fo
 };
 }  // namespace
 
-Lowered lower_model(const Universe& u, const LowerOptions& opt) {
+Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
+    LowerOptions opt = opt_in;
+    // the RK probe only reads u0 > 1/2; for uniforms (w + 1/2) 2^-32 that is the top bit of the word w (sde_u0_t)
+    opt.u0_bits = !opt.strict && opt.scheme == SCHEME_RK && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_PHILOX);
     const int P = u.P(), K = u.K();
     if (opt.f32 && opt.strict)
         throw ExprError{"dtype f32 needs arithmetic=\"fast\" (strict reproduces the reference's f64 operation order)"};
@@ -362,9 +608,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     StepGen gen(u, opt);
     gen.generate(L.enter_eq ? CUR : OLD, body);
     // Per-step constants that do not move along the time grid become literals (no table read in the step loop):
-    // bit-identical values always; under arithmetic=fast also values that agree to 2^-44 relative (a uniform grid
-    // k/D gives sqrt(dt) values a few ulp apart), replaced by their median — <= 1e-13 relative in a coefficient
-    // that is multiplied by sqrt(dt) z, far inside that mode's stated <= ~3 ulp per step.
+    // bit-identical values always; under arithmetic=fast also values that agree to 2^-44 relative, or to what moving the
+    // time points by a few ulp would change (StepGen::slot_tol: a uniform grid k/D gives dt and sqrt(dt) values a few ulp
+    // of t_end apart), replaced by their median — far inside that mode's stated <= ~3 ulp per step.
     std::vector<std::string> slot_macro(gen.slots.size());
     std::vector<std::string> table_slots;
     for (size_t i = 0; i < gen.slots.size(); ++i) {
@@ -372,12 +618,13 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
         std::sort(v.begin(), v.end());
         const double lo = v.front(), hi = v.back(), med = v[v.size() / 2];
         const bool same = lo == hi;
-        const bool close = !opt.strict && std::isfinite(lo) && std::isfinite(hi) && (hi - lo) <= std::ldexp(std::fabs(med), -44);
+        const bool close = !opt.strict && std::isfinite(lo) && std::isfinite(hi) &&
+                           (hi - lo) <= std::max(std::ldexp(std::fabs(med), -44), gen.slot_tol[i]);
         if (same || close) {
             // f64 plans: as a uniform-datapath value (sde_uc, sde_expr_helpers.cuh) so that fma(SLOT, z, g) reads two
             // register pairs, not three
             // register pairs, not three.  Slot 0 of a process is the addend the factor terms accumulate onto: a plain literal.
-            const bool multiplier = gen.slots[i].find("sqrt_dt") != std::string::npos;
+            const bool multiplier = gen.slot_mult[i];
             slot_macro[i] = (opt.f32 || !multiplier) ? "(" + format_real(med) + ")" : "sde_uc(" + format_real(med) + ")";
         } else {
             slot_macro[i] = "((sde_real)ss[" + std::to_string(4 + table_slots.size()) + "])";
@@ -539,6 +786,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     }
     s << "#define SDE_ICDF " << opt.icdf << "\n#define SDE_STRICT " << (opt.strict ? 1 : 0) << "\n";
     s << "#define SDE_NEEDS_U0 " << (opt.scheme == SCHEME_RK ? 1 : 0) << "\n";
+    if (opt.u0_bits) s << "#define SDE_U0_BITS 1\n";
     s << "#define SDE_BLOCK " << L.block << "\n#define SDE_MIN_BLOCKS " << L.min_blocks << "\n";
     if (L.wide) {
         s << "#define SDE_S " << (u.T() - 1) << "\n#define SDE_WNB " << L.wide_nb << "\n#define SDE_WNKK " << L.wide_nkk
@@ -599,7 +847,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt) {
     }
     for (size_t i = 0; i < slot_macro.size(); ++i) s << "#define SDE_SLOT_" << i << " " << slot_macro[i] << "\n";
     s << "__device__ __forceinline__ void sde_model_step(sde_real (&row)[SDE_P], sde_real (&c)[SDE_P], double& ct, const sde_real (&zu)[SDE_KK],\n"
-         "                                               const sde_real u0, const double* __restrict__ ss) {\n";
+         "                                               const sde_u0_t u0, const double* __restrict__ ss) {\n";
     s << "    const sde_real t_cur = (sde_real)ss[0], t_next = (sde_real)ss[1], dt = (sde_real)ss[2], sqrt_dt = (sde_real)ss[3];\n";
     s << "    (void)u0; (void)t_cur; (void)t_next; (void)dt; (void)sqrt_dt; (void)zu; (void)ct;\n";
     if (L.wide) s << "    // (the step lives in sde_sim_wide.cuh: X_i *= 1 + a_i dt + sqrt(dt) sum_k M[i][k] z_k on the FP64 tensor path)\n";

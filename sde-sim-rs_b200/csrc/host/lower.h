@@ -22,6 +22,7 @@ struct LowerOptions {
     int icdf = 0;            // 0 reference, 1 fast, 2 single (FP32 evaluation)
     bool strict = true;      // no FMA contraction in model arithmetic
     bool rk_textbook = false;
+    bool u0_bits = false;    // set by lower_model: the RK probe uniform reaches the step as its 32-bit word (sde_u0_t)
     bool f32 = false;        // dtype f32: state, model arithmetic and stored rows in single precision (needs !strict)
     int block = 0;           // 0 = auto
     int tile_steps = 0;      // 0 = auto

@@ -15,6 +15,18 @@ typedef float sde_real;
 typedef double sde_real;
 #endif
 
+// sde_u0_t: how the kernels hand the Runge-Kutta probe uniform u0 (runge_kutta.rs:18-22) to the step.  The step only asks
+// u0 > 1/2.  Where the uniform is u0 = (w + 1/2) 2^-32 of a 32-bit word w (Sobol xor / none, Philox) that is exactly the top
+// bit of w, so under arithmetic = fast the lowering defines SDE_U0_BITS and the kernels pass w itself: no conversion.
+#ifndef SDE_U0_BITS
+#define SDE_U0_BITS 0
+#endif
+#if SDE_U0_BITS
+typedef unsigned int sde_u0_t;
+#else
+typedef sde_real sde_u0_t;
+#endif
+
 // sde_uc(v): the f64 constant v as a value of the UNIFORM datapath.
 // On sm_100a a DFMA reads its register operands at one 64-bit pair per cycle (tools/ubench/dfma_operands.cu: three
 // distinct register pairs = 3 cycles per warp instruction and sub-partition, two pairs or a uniform-register /
@@ -67,6 +79,23 @@ __device__ __forceinline__ double sde_f_sqrt_fast(double x) {
     return (fabs(x) >= 2.2250738585072014e-308) ? t : x * 0.0;
 }
 __device__ __forceinline__ float sde_f_sqrt_fast(float x) { return sqrtf(x); }
+// max(x, 0)^0.5 under arithmetic = fast (the full-truncation root of square-root diffusions), same value as
+// sde_f_sqrt_fast(sde_f_max(x, 0.0)): NaN stays NaN, x <= 0 and subnormals give 0, +inf passes through.  The four FP64 compares
+// of the two separate guards become integer tests of the high word, which do not occupy the FP64 pipe: 5 FP64 instructions.
+__device__ __forceinline__ double sde_f_sqrt_max0_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y, e = fma(-g, y, 1.0);
+    const double r = fma(g, e * fma(e, 0.375, 0.5), g);
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const bool normal = (unsigned)(hi - 0x00100000) < 0x7fe00000u;                                                   // positive, finite, not subnormal
+    const bool pass = hi >= 0x7ff00000 || (unsigned)hi > 0xfff00000u || ((unsigned)hi == 0xfff00000u && lo != 0);    // +inf, NaN of either sign
+    return normal ? r : (pass ? x : 0.0);
+}
+// v with its sign flipped where the mask's top bit is set (mask = 0 or 0x80000000): products with sk = +-1 of the
+// Runge-Kutta probe (runge_kutta.rs:18-22) without an FP64 instruction
+__device__ __forceinline__ double sde_f_xorsign(double v, unsigned int m) { return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v)); }
+__device__ __forceinline__ float sde_f_xorsign(float v, unsigned int m) { return __int_as_float(__float_as_int(v) ^ (int)m); }
 
 // ---- f32 overloads (dtype = f32 plans; arithmetic = fast only, so no *_rn intrinsics are needed)
 __device__ __forceinline__ float sde_f_sq(float x) { return x * x; }

@@ -288,9 +288,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         //   draw(t, j, ..)    uniforms -> normal / Poisson draws of step t (j = position in the group; it must be a
         //                     compile-time constant after unrolling so the ChaCha buffer is indexed statically)
         //   advance(t, ..)    one step of the scheme + staging of the new row
-        auto draw = [&](const int t, const int j, sde_real (&zu)[SDE_KK], sde_real& u0) __attribute__((always_inline)) {
+        auto draw = [&](const int t, const int j, sde_real (&zu)[SDE_KK], sde_u0_t& u0) __attribute__((always_inline)) {
             const int tl = t - t0;
-            u0 = 0.0;
+            u0 = (sde_u0_t)0;
             zu[0] = 0.0;
             (void)tl; (void)j;
 #if SDE_RNG == 4
@@ -344,7 +344,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #elif SDE_RNG == 2 || SDE_RNG == 5
                 // digital shift: u = ((x ^ mask) + 1/2) * 2^-32, one 32-bit mask per dimension (already folded into x);
                 // Philox words take the same 32-bit form
+#if SDE_U0_BITS
+                if (k == 0 && SDE_NEEDS_U0) u0 = x;           // the step reads u0 > 1/2 = the top bit of x (sde_u0_t)
+#else
                 if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+#endif
                 if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1
                     zu[k] = sde_icdf_normal_fast_k32(x, s_icdf, lane);
@@ -397,7 +401,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #else
         auto draw_fixup = [&](const int, const int, sde_real (*)[SDE_KK]) __attribute__((always_inline)) {};
 #endif
-        auto advance = [&](const int t, const sde_real (&zu)[SDE_KK], const sde_real u0) __attribute__((always_inline)) {
+        auto advance = [&](const int t, const sde_real (&zu)[SDE_KK], const sde_u0_t u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
 #if SDE_OUT == 0 && !SDE_DIRECT
@@ -415,7 +419,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         sde_real* group_dst = my_row;                           // running store pointer of the step groups
 #endif
         auto group = [&](const int tc) __attribute__((always_inline)) {
-            sde_real zu[SDE_UNR][SDE_KK], u0[SDE_UNR];
+            sde_real zu[SDE_UNR][SDE_KK];
+            sde_u0_t u0[SDE_UNR];
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) draw(tc + j, j, zu[j], u0[j]);
             draw_fixup(tc, SDE_UNR, zu);
@@ -452,7 +457,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
         // one step on its own (ragged ends); direct mode stores its row element-wise
         auto single = [&](const int t, const int j) __attribute__((always_inline)) {
-            sde_real zu[1][SDE_KK], u0;
+            sde_real zu[1][SDE_KK];
+            sde_u0_t u0;
             draw(t, j, zu[0], u0);
             draw_fixup(t, 1, zu);
             advance(t, zu[0], u0);

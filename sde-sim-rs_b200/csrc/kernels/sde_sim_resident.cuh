@@ -217,7 +217,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                                      : prm.partials + (size_t)(((long long)s_local * T * SDE_P) & 3);
 
         // draw_word: the (digitally shifted, possibly sign-folded) 32-bit word of factor k -> normal / Poisson draw
-        auto draw_word = [&](const sde_u32 w, const int k, double& z, double& u0) __attribute__((always_inline)) {
+        auto draw_word = [&](const sde_u32 w, const int k, double& z, sde_u0_t& u0) __attribute__((always_inline)) {
 #if SDE_RES_FOLD
             // w is the folded integer of p = (x + 1/2) 2^-32: every factor is Wiener, nothing else reads the uniform
 #if SDE_ICDF_WIDE
@@ -228,7 +228,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             (void)k; (void)u0;
 #elif SDE_RNG == 2
             const sde_u32 x = w;
+#if SDE_U0_BITS
+            if (k == 0 && SDE_NEEDS_U0) u0 = x;               // the step reads u0 > 1/2 = the top bit of x (sde_u0_t)
+#else
             if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+#endif
             // digital shift: u = (x + 1/2) * 2^-32 in (0, 1)
             if (sde_factor_is_wiener(k)) {
 #if SDE_ICDF == 1 && SDE_ICDF_WIDE
@@ -264,8 +268,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // draw_x: draws of step t on its own (row heads / tails).  `flip[k]` is XORed into the word of factor k: zero for
         // the lane's own path, (the folded form of) V_d[ctz(n + 1)] for the path that follows it
         // (x_d(n+1) = x_d(n) ^ V_d[ctz(n+1)], and folding is linear)
-        auto draw_x = [&](const int t, const sde_u32 (&flip)[SDE_KK], double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
-            u0 = 0.0;
+        auto draw_x = [&](const int t, const sde_u32 (&flip)[SDE_KK], double (&zu)[SDE_KK], sde_u0_t& u0) __attribute__((always_inline)) {
+            u0 = (sde_u0_t)0;
             zu[0] = 0.0;
 #ifdef SDE_DEBUG_NOCOMPUTE
             zu[0] = (double)t * 1e-4;                         // profiling aid: stores only (no Sobol reads, no inverse normal)
@@ -277,7 +281,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 draw_word(bw_word(d) ^ lane_word(d) ^ flip[k], k, zu[k], u0);
             }
         };
-        auto draw = [&](const int t, double (&zu)[SDE_KK], double& u0) __attribute__((always_inline)) {
+        auto draw = [&](const int t, double (&zu)[SDE_KK], sde_u0_t& u0) __attribute__((always_inline)) {
             sde_u32 none[SDE_KK];
 #pragma unroll
             for (int k = 0; k < SDE_KK; ++k) none[k] = 0u;
@@ -287,10 +291,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // either table — one 128-bit load per quad (lane table: conflict free; warp part: broadcast).  Quad q of the lane
         // table is 512 bytes, of the warp part 16 bytes, and q = (tg K + off) / 4: both addresses are one multiply-add on
         // the step counter (written as opaque PTX so that they are not turned into extra loop-carried pointers)
-        auto draw_group = [&](const int tg, double (&zu)[SDE_RES_GRP][SDE_KK], double (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
+        auto draw_group = [&](const int tg, double (&zu)[SDE_RES_GRP][SDE_KK], sde_u0_t (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
 #ifdef SDE_DEBUG_NOCOMPUTE
 #pragma unroll
-            for (int j = 0; j < SDE_RES_GRP; ++j) { u0[j] = 0.0; zu[j][0] = (double)(tg + j) * 1e-4; }
+            for (int j = 0; j < SDE_RES_GRP; ++j) { u0[j] = (sde_u0_t)0; zu[j][0] = (double)(tg + j) * 1e-4; }
             return;
 #endif
             sde_u32 la, ba;
@@ -306,7 +310,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             }
 #pragma unroll
             for (int j = 0; j < SDE_RES_GRP; ++j) {
-                u0[j] = 0.0;
+                u0[j] = (sde_u0_t)0;
                 zu[j][0] = 0.0;
 #pragma unroll
                 for (int k = 0; k < SDE_K; ++k) draw_word(lw[j * SDE_K + k] ^ bw[j * SDE_K + k], k, zu[j][k], u0[j]);
@@ -314,7 +318,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         };
         // one step on its own (the <= 3 steps before the first and after the last aligned group)
         auto single = [&](const int t) __attribute__((always_inline)) {
-            double zu[SDE_KK], u0;
+            double zu[SDE_KK];
+            sde_u0_t u0;
             draw(t, zu, u0);
             sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
 #ifndef SDE_DEBUG_NOSCALAR
@@ -340,7 +345,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         hv[0] = row[0];
 #pragma unroll 1
         for (; t < g_eff; ++t) {
-            double zu[SDE_KK], u0;
+            double zu[SDE_KK];
+            sde_u0_t u0;
             draw(t, zu, u0);
             sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
             if (t == 0) hv[1] = row[0]; else if (t == 1) hv[2] = row[0]; else hv[3] = row[0];
@@ -373,7 +379,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
         // advance_group: the sequential state updates of one group (rows t+1 .. t+GRP collected in output order) and
         // their full-sector stores (pad lanes write the scratch row)
-        auto advance_group = [&](const int tg, const double (&zu)[SDE_RES_GRP][SDE_KK], const double (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
+        auto advance_group = [&](const int tg, const double (&zu)[SDE_RES_GRP][SDE_KK], const sde_u0_t (&u0)[SDE_RES_GRP]) __attribute__((always_inline)) {
             double vals[SDE_RES_GRP * SDE_P];
 #pragma unroll
             for (int j = 0; j < SDE_RES_GRP; ++j) {
@@ -404,7 +410,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // (serial) state updates of group g, so the dependent multiply chain and the stores hide behind them
         // (two register sets, ping-pong: no copies on the loop back edge)
         if (n_groups > 0) {
-            double za[SDE_RES_GRP][SDE_KK], ua[SDE_RES_GRP], zb[SDE_RES_GRP][SDE_KK], ub[SDE_RES_GRP];
+            double za[SDE_RES_GRP][SDE_KK], zb[SDE_RES_GRP][SDE_KK];
+            sde_u0_t ua[SDE_RES_GRP], ub[SDE_RES_GRP];
             draw_group(t, za, ua);
 #pragma unroll 1
             for (; t + 3 * SDE_RES_GRP <= t_last; t += 2 * SDE_RES_GRP) {   // the step counter is the only loop-carried integer
@@ -427,7 +434,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll 1
         for (int gi = 0; gi < n_groups; ++gi, t += SDE_RES_GRP) {
             // phase 1: the state-independent uniform -> normal chains of the group (independent instruction streams)
-            double zu[SDE_RES_GRP][SDE_KK], u0[SDE_RES_GRP];
+            double zu[SDE_RES_GRP][SDE_KK];
+            sde_u0_t u0[SDE_RES_GRP];
             draw_group(t, zu, u0);
             advance_group(t, zu, u0);
         }
@@ -440,7 +448,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             tv[0] = tv[1] = tv[2] = 0.0;
 #pragma unroll 1
             for (; t < S; ++t) {
-                double zu[SDE_KK], u0;
+                double zu[SDE_KK];
+            sde_u0_t u0;
                 draw(t, zu, u0);
                 sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
                 if (t == t_tail) tv[0] = row[0]; else if (t == t_tail + 1) tv[1] = row[0]; else tv[2] = row[0];
@@ -461,7 +470,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                         for (int k = 0; k < SDE_K; ++k)       // V_d[b] = nibble-table entry of the single-bit nibble value
                             flip[k] = sde_res_fold(__ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k)));
-                        double zu[SDE_KK], u0;
+                        double zu[SDE_KK];
+            sde_u0_t u0;
                         draw_x(j, flip, zu, u0);
                         sde_model_step(row2, cache2, ct2, zu, u0, s_step + j * SDE_STEP_LD);
                         if (j == 0) nh[1] = row2[0]; else nh[2] = row2[0];

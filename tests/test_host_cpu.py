@@ -86,13 +86,42 @@ def _lower(eqs, times, scheme, rng, compile=1, **kw):
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant=kw.get("rk_variant", "reference"),
                         ntp_direct=kw.get("ntp_direct", 0), dtype=kw.get("dtype", "f64"), wide_mma=kw.get("wide_mma", 0),
-                        block_threads=kw.get("block_threads", 0), tile_steps=kw.get("tile_steps", 0))
+                        block_threads=kw.get("block_threads", 0), tile_steps=kw.get("tile_steps", 0),
+                        generator=kw.get("generator", "chacha8"))
     src, nb = C.c_void_p(), C.c_size_t(0)
     rc = _ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), compile, C.byref(src), C.byref(nb))
     _ffi.check(rc)
     text = C.string_at(src).decode()
     _ffi.lib().sde_free_string(src)
     return text, nb.value
+
+
+def test_fast_arithmetic_factors_the_heston_step():
+    """arithmetic=fast: coefficients in product form, terms grouped by their state-dependent part, constants folded into
+    per-step slots (lower.cpp, factorise) — the Heston RK step (C3) is what the FP64 pipe spends its time on."""
+    fast = dict(scramble="xor", icdf="fast", arithmetic="fast")
+    text, _ = _lower(HESTON_EQ, grid(1000), "runge-kutta", "sobol", compile=0, **fast)
+    step = text.split("sde_model_step(")[1]
+    assert "#define SDE_U0_BITS 1" in text and "const sde_u0_t u0" in text and "(~u0) & 0x80000000u" in step
+    assert step.count("sde_f_sqrt_max0_fast(c[1])") == 2                 # one root per stage, shared by dS and dv
+    assert "sde_f_max" not in step and "sde_f_sqrt_fast" not in step
+    assert "fma(q0, w0_1, w0_0)" in step and "(f1_0 * i1_0)" in step     # dS: S * (a + sqrt(v+) b z)
+    assert "fma(SDE_SLOT_5, zu[1], (SDE_SLOT_4 * zu[0]))" in step        # dv: both Wiener terms share sqrt(v+)
+    # the uniform grid's dt / sqrt(dt) became literals: 0.05 dt, 2 dt, (-0.21 + 0.2142...) sqrt(dt)
+    assert "sde_uc(5.000000000000005e-05)" in text and "sde_uc(0.0020000000000000018)" in text and "ss[4]" not in text
+    # a non-uniform grid keeps them in the per-step table
+    times = [0.0] + list(np.cumsum(np.linspace(1e-3, 2e-3, 40)))
+    tab, _ = _lower(HESTON_EQ, times, "runge-kutta", "sobol", compile=0, **fast)
+    assert "slots[0] = (0.050000000000000003 * dt);" in tab and "((sde_real)ss[4])" in tab
+    # raw Sobol points (u = x / 2^32 can equal 1/2 exactly) and the ChaCha stream keep the f64 compare
+    raw, _ = _lower(HESTON_EQ, grid(250), "runge-kutta", "sobol", compile=0, scramble="none", icdf="fast", arithmetic="fast")
+    assert "SDE_U0_BITS" not in raw and "(u0 > 0.5) ? 0u : 0x80000000u" in raw
+    # strict arithmetic keeps the reference's term-by-term order
+    strict, _ = _lower(HESTON_EQ, grid(1000), "runge-kutta", "sobol", compile=0, scramble="xor")
+    assert "SDE_U0_BITS" not in strict and "sde_f_max(c[1], 0.0)" in strict and "__dmul_rn" in strict
+    # Euler, non-linear process: same grouping
+    eul, _ = _lower(HESTON_EQ, grid(250), "euler", "sobol", compile=0, **fast)
+    assert eul.split("sde_model_step(")[1].count("sde_f_sqrt_max0_fast(c[1])") == 2   # one per process block
 
 
 def test_unknown_scheme_is_value_error():
@@ -104,10 +133,15 @@ def test_f32_needs_fast_arithmetic_and_emits_float_literals():
     with pytest.raises(ValueError, match="f32 needs arithmetic"):
         _lower(GBM_EQ, grid(252, 4), "euler", "pseudo", compile=0, dtype="f32")
     text, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, dtype="f32", arithmetic="fast")
-    assert "#define SDE_F32 1" in text and "0.0500000007f" in text and "0.5f" in text
-    assert "0.05 " not in text.split("sde_model_step(")[1]             # no f64 literal inside the model step
+    # (arithmetic=fast folds 0.05 into the per-step constant 0.05 * dt, emitted as a single-precision literal)
+    assert "#define SDE_F32 1" in text and "0.000198412701f" in text and "0.5f" in text
+    import re
+    step = text.split("sde_model_step(")[1]
+    assert not re.search(r"\d\.\d+(e-?\d+)?(?![\df])\b", step.split("{", 1)[1])   # no f64 literal inside the model step
     text64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, arithmetic="fast")
-    assert "SDE_F32" not in text64 and "0.050000000000000003" in text64
+    assert "SDE_F32" not in text64 and "sde_uc(0.0001984126984126984" in text64
+    strict64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0)
+    assert "0.050000000000000003" in strict64 and "__dmul_rn" in strict64
 
 
 @pytest.mark.parametrize("block", [16, 100, 160 + 1, 2048, -32])
@@ -181,10 +215,23 @@ def test_lowering_cache_rule_euler_vs_rk():
     ("C2-tpn", GBM_EQ, grid(252), "euler", "sobol", {"scramble": "xor", "layout": "TPN"}),
     ("C3", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor"}),
     ("C3-terminal", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal"}),
+    # arithmetic=fast Runge-Kutta (factored form, probe uniform passed as its 32-bit word) on every kernel that can run it
+    ("C3-fast-tiled", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast"}),
+    ("C3-fast-resident", HESTON_EQ, grid(250), "runge-kutta", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast"}),
+    ("C3-fast-raw", HESTON_EQ, grid(250), "runge-kutta", "sobol", {"scramble": "none", "icdf": "fast", "arithmetic": "fast"}),
+    ("C3-fast-philox", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal", "icdf": "fast", "arithmetic": "fast", "generator": "philox"}),
+    ("C3-fast-f32", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor", "icdf": "single", "arithmetic": "fast", "dtype": "f32"}),
+    ("C3-fast-cp", HESTON_EQ, grid(100), "runge-kutta", "sobol", {"icdf": "fast", "arithmetic": "fast"}),
     ("C5", GBM_EQ, grid(365), "euler", "pseudo", {"output": "moments", "icdf": "fast"}),
     ("jump", ["dX0 = ( 2.0 * (0.5 - X0) ) * dt + ( 0.1 ) * dW1",
               "dX1 = ( 0.01 * X1 ) * dt + ( 0.2 * X1 ) * dW2 + ( 0.5 * cos(t) ) * dN1(abs(X0) * 40)",
               "C = max(X1 - 100.0, 0.0) + X0"], grid(50, 15), "runge-kutta", "pseudo", {}),
+    ("jump-fast-rk", ["dX0 = ( 2.0 * (0.5 - X0) ) * dt + ( 0.1 ) * dW1",
+                      "dX1 = ( 0.01 * X1 ) * dt + ( 0.2 * X1 ) * dW2 + ( 0.5 * cos(t) ) * dN1(abs(X0) * 40)",
+                      "C = max(X1 - 100.0, 0.0) + X0"], grid(50, 15), "runge-kutta", "pseudo", {"arithmetic": "fast", "icdf": "fast"}),
+    ("jump-fast-euler", ["dX0 = ( 2.0 * (0.5 - X0) ) * dt + ( 0.1 ) * dW1",
+                         "dX1 = ( 0.01 * X1 ) * dt + ( 0.2 * X1 ) * dW2 + ( 0.5 * cos(t) ) * dN1(abs(X0) * 40)",
+                         "C = max(X1 - 100.0, 0.0) + X0"], grid(50, 15), "euler", "sobol", {"scramble": "xor", "arithmetic": "fast", "icdf": "fast"}),
 ])
 def test_configs_lower_and_compile_for_sm100a(name, eqs, times, scheme, rng, kw):
     text, nbytes = _lower(eqs, times, scheme, rng, compile=1, **kw)     # NVRTC --gpu-architecture=sm_100a, no GPU needed

@@ -299,7 +299,9 @@ class StepGen {
         return acc;
     }
     // a per-step constant kappa * dt or kappa * sqrt(dt): table slot / literal when hoisted, else computed in place
-    std::string step_const(double kappa, bool sqrt_of_dt) {
+    // `uniform`: the constant is the only non-register operand of a three-operand FMA (kept on the uniform datapath, sde_uc);
+    // constants that feed a multiply, a sign flip or an FMA that has another constant stay literals — uniform registers are few
+    std::string step_const(double kappa, bool sqrt_of_dt, bool uniform) {
         const std::string expr = "(" + format_real(kappa) + (sqrt_of_dt ? " * sqrt_dt)" : " * dt)");
         if (!hoist_) return expr;
         const int S = u_.T() - 1;
@@ -307,7 +309,7 @@ class StepGen {
         for (int q = 0; q < S; ++q) { const double dt = u_.times[q + 1] - u_.times[q]; v[q] = kappa * (sqrt_of_dt ? std::sqrt(dt) : dt); }
         slots.push_back(expr);
         slot_values.push_back(v);
-        slot_mult.push_back(true);
+        slot_mult.push_back(uniform);
         slot_tol.push_back(grid_tol(kappa, sqrt_of_dt));
         return "SDE_SLOT_" + std::to_string(slots.size() - 1);
     }
@@ -325,10 +327,12 @@ class StepGen {
                 if (t.kind == IncKind::Time) kdt += F.kappa[j];
                 if (t.kind == IncKind::Wiener) { kw[t.factor] += F.kappa[j]; used[t.factor] = true; ksum += F.kappa[j]; }
             }
-            std::string acc = g.has_dt ? step_const(kdt, false) : "";
+            bool alone = true;                               // W_g is the bare dt constant: an FMA operand of the stage sums
+            for (size_t j : g.terms) if (pr.terms[j].kind != IncKind::Time) alone = false;
+            std::string acc = g.has_dt ? step_const(kdt, false, alone) : "";
             for (int k = 0; k < u_.K(); ++k) {
                 if (!used[k]) continue;
-                const std::string b = step_const(kw[k], true), z = "zu[" + std::to_string(k) + "]";
+                const std::string b = step_const(kw[k], true, !acc.empty()), z = "zu[" + std::to_string(k) + "]";
                 acc = acc.empty() ? "(" + b + " * " + z + ")" : "fma(" + b + ", " + z + ", " + acc + ")";
             }
             for (size_t j : g.terms) {
@@ -338,7 +342,7 @@ class StepGen {
             }
             const std::string id = std::to_string(p) + "_" + std::to_string(gi);
             line("const sde_real w" + id + " = " + acc + ";");
-            if (rk && g.has_wiener) line("const sde_real pw" + id + " = sde_f_xorsign((sde_real)" + step_const(ksum, true) + ", skm);");
+            if (rk && g.has_wiener) line("const sde_real pw" + id + " = sde_f_xorsign((sde_real)" + step_const(ksum, true, false) + ", skm);");
         }
     }
     // sum_g (V_g / F) * weight_g over the groups that have the weight (fma chain onto the factor-free group)

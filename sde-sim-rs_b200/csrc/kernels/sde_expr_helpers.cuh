@@ -81,16 +81,16 @@ __device__ __forceinline__ double sde_f_sqrt_fast(double x) {
 __device__ __forceinline__ float sde_f_sqrt_fast(float x) { return sqrtf(x); }
 // max(x, 0)^0.5 under arithmetic = fast (the full-truncation root of square-root diffusions), same value as
 // sde_f_sqrt_fast(sde_f_max(x, 0.0)): NaN stays NaN, x <= 0 and subnormals give 0, +inf passes through.  The four FP64 compares
-// of the two separate guards become integer tests of the high word, which do not occupy the FP64 pipe: 5 FP64 instructions.
+// of the two separate guards become one integer test of the high word and one FP64 compare: 6 FP64 instructions.
 __device__ __forceinline__ double sde_f_sqrt_max0_fast(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double g = x * y, e = fma(-g, y, 1.0);
     const double r = fma(g, e * fma(e, 0.375, 0.5), g);
-    const int hi = __double2hiint(x), lo = __double2loint(x);
-    const bool normal = (unsigned)(hi - 0x00100000) < 0x7fe00000u;                                                   // positive, finite, not subnormal
-    const bool pass = hi >= 0x7ff00000 || (unsigned)hi > 0xfff00000u || ((unsigned)hi == 0xfff00000u && lo != 0);    // +inf, NaN of either sign
-    return normal ? r : (pass ? x : 0.0);
+    const bool normal = (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;    // positive, finite, not subnormal
+    const bool pass = !(x < __longlong_as_double(0x7ff0000000000000ll));             // +inf and NaN (either sign): returned as they are
+    const double z = pass ? x : 0.0;                                                 // x <= 0 (also -inf), subnormals
+    return normal ? r : z;
 }
 // v with its sign flipped where the mask's top bit is set (mask = 0 or 0x80000000): products with sk = +-1 of the
 // Runge-Kutta probe (runge_kutta.rs:18-22) without an FP64 instruction

@@ -101,6 +101,21 @@ __device__ __forceinline__ sde_real sde_uniform_to_draw(double u, bool wiener, c
 #endif
 }
 
+// 32-bit-word uniforms (Sobol digital shift / raw-free modes, Philox) with the fast inverse normal: the shared-window entry
+// points of sde_device_icdf.cuh (one LDS.128 per draw, exponent term by conversion, FP32-unit seeds).  For the Sobol
+// digital shift the staged CTA/warp and lane words are SIGN-FOLDED, y = x ^ ((x >>s 31) & 0x7fffffff): GF(2)-linear like
+// the Sobol map itself, so their XOR is the folded integer of the path's uniform (bit 31: p >= 1/2, bits 30..0: those of
+// min(p, 1-p)) and the draw starts from it without sign-mask / conditional-complement instructions.
+#define SDE_TILED_W32 ((SDE_RNG == 2 || SDE_RNG == 5) && SDE_ICDF == 1)
+#define SDE_TILED_FOLD (SDE_RNG == 2 && SDE_ICDF == 1)
+__device__ __forceinline__ sde_u32 sde_tile_fold(sde_u32 x) {
+#if SDE_TILED_FOLD
+    return x ^ ((sde_u32)((int)x >> 31) & 0x7fffffffu);
+#else
+    return x;
+#endif
+}
+
 // Registers that carry the next tile's staged data from the moment its loads are issued to the moment
 // they are written to shared memory (static indexing only).
 struct SdeTilePrefetch {
@@ -144,7 +159,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     (void)s_global;
 
 #if SDE_ICDF == 1 && SDE_RNG != 4
-    sde_icdf_table_load(s_icdf, tid, SDE_BLOCK);
+    sde_icdf_table_load(s_icdf, tid, SDE_BLOCK, SDE_TILED_W32 ? SDE_ICDF_Y_OFFSET_K32 : 0.0);
+#endif
+#if SDE_TILED_W32
+    const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_icdf + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
 #endif
 
     // ---- staging of one tile's read-only data (see header).  issue(): global loads into registers;
@@ -217,12 +235,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         for (int i = 0; i < SDE_PF_BW; ++i) {
             const int e = tid + i * SDE_BLOCK;
             if (e < SDE_TS * SDE_KK * SDE_NW)
-                bw[e] = ((pf.bw[i][0] ^ pf.bw[i][1]) ^ (pf.bw[i][2] ^ pf.bw[i][3])) ^ ((pf.bw[i][4] ^ pf.bw[i][5]) ^ (pf.bw[i][6] ^ pf.bw[i][7])) ^ pf.bw[i][8];
+                bw[e] = sde_tile_fold(((pf.bw[i][0] ^ pf.bw[i][1]) ^ (pf.bw[i][2] ^ pf.bw[i][3])) ^ ((pf.bw[i][4] ^ pf.bw[i][5]) ^ (pf.bw[i][6] ^ pf.bw[i][7])) ^ pf.bw[i][8]);
         }
 #pragma unroll
         for (int i = 0; i < SDE_PF_LANE; ++i) {
             const int e = tid + i * SDE_BLOCK;
-            if (e < SDE_TS * SDE_KK * 32) ln[e] = pf.ln[i];
+            if (e < SDE_TS * SDE_KK * 32) ln[e] = sde_tile_fold(pf.ln[i]);
         }
 #endif
     };
@@ -343,22 +361,24 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 }
 #elif SDE_RNG == 2 || SDE_RNG == 5
                 // digital shift: u = ((x ^ mask) + 1/2) * 2^-32, one 32-bit mask per dimension (already folded into x);
-                // Philox words take the same 32-bit form
+                // Philox words take the same 32-bit form.  Under SDE_TILED_FOLD `x` is the sign-folded word (see above).
 #if SDE_U0_BITS
-                if (k == 0 && SDE_NEEDS_U0) u0 = x;           // the step reads u0 > 1/2 = the top bit of x (sde_u0_t)
+                if (k == 0 && SDE_NEEDS_U0) u0 = x;           // the step reads u0 > 1/2 = the top bit of x, folded or not (sde_u0_t)
 #else
-                if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+                if (k == 0 && SDE_NEEDS_U0) u0 = fma((double)sde_tile_fold(x), 2.3283064365386963e-10, 1.1641532182693481e-10);
 #endif
                 if (sde_factor_is_wiener(k)) {
-#if SDE_ICDF == 1
-                    zu[k] = sde_icdf_normal_fast_k32(x, s_icdf, lane);
+#if SDE_TILED_FOLD
+                    zu[k] = sde_icdf_normal_fast_y32s(x, tab_lane);
+#elif SDE_TILED_W32
+                    zu[k] = sde_icdf_normal_fast_k32s(x, tab_lane);
 #elif SDE_ICDF == 2
                     zu[k] = sde_icdf_normal_single_k32(x);
 #else
                     zu[k] = sde_icdf_normal_reference(fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10));
 #endif
                 } else {
-                    zu[k] = fma((double)x, 2.3283064365386963e-10, 1.1641532182693481e-10);
+                    zu[k] = fma((double)sde_tile_fold(x), 2.3283064365386963e-10, 1.1641532182693481e-10);   // (folding is an involution)
                 }
 #else
                 double u;
@@ -436,7 +456,11 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                 // predicated (not branched) stores: dead lanes only exist in the first and last CTA
                 sde_real* dst = group_dst;                      // = my_row + (tc + 1) P: 32-byte aligned by the choice of gamma
                 group_dst += 4 * SDE_P;
+#ifdef SDE_DEBUG_NOSTORE
+                const int live = (int)gridDim.z - 1;            // profiling aid: the stores stay in the code, predicated off at run time
+#else
                 const int live = valid ? 1 : 0;
+#endif
 #pragma unroll
                 for (int q = 0; q < SDE_P; ++q) {
 #if SDE_ST256

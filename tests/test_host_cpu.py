@@ -139,7 +139,7 @@ def test_f32_needs_fast_arithmetic_and_emits_float_literals():
     step = text.split("sde_model_step(")[1]
     assert not re.search(r"\d\.\d+(e-?\d+)?(?![\df])\b", step.split("{", 1)[1])   # no f64 literal inside the model step
     text64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0, arithmetic="fast")
-    assert "SDE_F32" not in text64 and "sde_uc(0.0001984126984126984" in text64
+    assert "SDE_F32" not in text64 and "(0.0001984126984126984" in text64 and "sde_uc(0.0062994078834871" in text64
     strict64, _ = _lower(GBM_EQ, grid(252, 4), "runge-kutta", "pseudo", compile=0)
     assert "0.050000000000000003" in strict64 and "__dmul_rn" in strict64
 

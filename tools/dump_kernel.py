@@ -26,6 +26,7 @@ CONFIGS = {
     "c5": (GBM, 365, "euler", "pseudo", dict(output="moments", icdf="fast", arithmetic="fast")),
     "c5p": (GBM, 365, "euler", "pseudo", dict(output="moments", icdf="fast", arithmetic="fast", generator="philox")),
     "c2cp": (GBM, 252, "euler", "sobol", dict(icdf="fast", arithmetic="fast")),
+    "c3t": (HESTON, 1000, "runge-kutta", "sobol", dict(scramble="xor", icdf="fast", arithmetic="fast", output="terminal")),
     "c3": (HESTON, 1000, "runge-kutta", "sobol", dict(scramble="xor", icdf="fast", arithmetic="fast")),
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Run one named BASELINE config a few times (device-resident output) and print its kernel time: the target of ncu
 captures and A/B timings of everything that is not the C2 headline.
-usage: run_cfg.py <c3|c3t|c2cp|c2tpn|c5|c5p> [runs]      env SDE_B200_DEFINES etc. are honoured by the lowering"""
+usage: run_cfg.py <c2|c3|c3t|c2cp|c2tpn|c5|c5p> [runs]      env SDE_B200_DEFINES etc. are honoured by the lowering"""
 import os
 import sys
 
@@ -17,6 +17,7 @@ fast = dict(icdf="fast", arithmetic="fast")
 CFG = {
     "c3": (HESTON_EQ, 1000, {"S": 100.0, "v": 0.04}, 1 << 22, "runge-kutta", "sobol", dict(output="paths", scramble="xor", **fast)),
     "c3t": (HESTON_EQ, 1000, {"S": 100.0, "v": 0.04}, 1 << 22, "runge-kutta", "sobol", dict(output="terminal", scramble="xor", **fast)),
+    "c2": (GBM_EQ, 252, {"X1": 1.0}, 1 << 24, "euler", "sobol", dict(output="paths", scramble="xor", **fast)),
     "c2cp": (GBM_EQ, 252, {"X1": 1.0}, 1 << 24, "euler", "sobol", dict(output="paths", **fast)),
     "c2tpn": (GBM_EQ, 252, {"X1": 1.0}, 1 << 24, "euler", "sobol", dict(output="paths", layout="TPN", scramble="xor", **fast)),
     "c5": (GBM_EQ, 365, {"X1": 1.0}, 1 << 28, "euler", "pseudo", dict(output="moments", **fast)),

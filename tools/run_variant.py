@@ -45,7 +45,7 @@ for spec in sys.argv[2:]:
                 pw.append(pynvml.nvmlDeviceGetFieldValues(nv, [pynvml.NVML_FI_DEV_POWER_INSTANT])[0].value.uiVal / 1000.0)
             except Exception:  # noqa: BLE001
                 pw.append(pynvml.nvmlDeviceGetPowerUsage(nv) / 1000.0)
-            time.sleep(0.005)
+            time.sleep(0.05)                             # (polling NVML at 200 Hz slowed the launches by 25 %: 20 Hz)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / runs
     extra = ""

@@ -25,6 +25,27 @@ __global__ void __launch_bounds__(1024, 1) k_sector(double* out, long long n_row
     }
 }
 
+// D: as A, but a lane collects NS sectors (NS*4 steps) and writes them back to back: complete 64- / 128-byte pieces reach L2 at once
+template <int NS>
+__global__ void __launch_bounds__(1024, 1) k_sector_burst(double* out, long long n_rows, int iters_dummy) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long n_items = n_rows / 32;
+    for (long long item = (long long)blockIdx.x * nw + warp; item < n_items; item += (long long)gridDim.x * nw) {
+        const long long s = ((item >> 2) << 7) + (item & 3) + 4 * lane;
+        double* row = out + s * T;
+        const int gamma = (int)((4 - ((s * T + 1) & 3)) & 3);
+        double v = (double)lane;
+        for (int t = gamma; t + 4 * NS <= T - 1; t += 4 * NS) {
+            double* dst = row + t + 1;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                v += 1.0;
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(v), "d"(v), "d"(v), "d"(v) : "memory");
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024, 1) k_tma(double* out, long long n_rows, int dummy) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -88,9 +109,12 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         printf("%-40s %.3f ms  %.0f GB/s  (%s)\n", name, ms / 5, bytes / (ms / 5) * 1e-6, cudaGetErrorString(cudaGetLastError()));
     };
-    for (int threads : {128, 256, 384, 512, 768}) {
+    for (int threads : {256, 512, 768, 1024}) {
         printf("threads/SM %d\n", threads);
         run("A sector per lane (rows 4 apart)", [&] { k_sector<<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 62 * 32);
+        run("D2 two sectors back to back", [&] { k_sector_burst<2><<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 31 * 64);
+        run("D4 four sectors back to back", [&] { k_sector_burst<4><<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 15 * 128);
+        run("D8 eight sectors back to back", [&] { k_sector_burst<8><<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 7 * 256);
         cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, threads * 288 + 128);
         run("B TMA bulk 128 B per lane (rows 16 apart)", [&] { k_tma<<<148, threads, threads * 288 + 128>>>(out, n_rows, 0); }, (double)n_rows * 14 * 128);
         run("C 4 lanes per 128 B line", [&] { k_line4<<<148, threads>>>(out, n_rows, 0); }, (double)n_rows * 14 * 128);

@@ -601,7 +601,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         }
         __syncwarp();
 #endif
+#ifndef SDE_DEBUG_NOBARRIER                                   // (profiling aid: results are garbage without it)
         __syncthreads();                                      // next tile's staged data visible; this tile's buffer free
+#endif
     }
 
 #if SDE_OUT == 2

@@ -86,6 +86,34 @@ struct NvrtcState {
     std::string why;
 };
 
+// Where the toolkit's NVRTC would be loaded from (see nvrtc_state): the two path candidates.
+void nvrtc_path_candidates(std::string* p1, std::string* p2) {
+    const std::string cuda_home = std::getenv("CUDA_HOME") ? std::getenv("CUDA_HOME") : "/usr/local/cuda";
+    *p1 = cuda_home + "/lib64/libnvrtc.so.12";
+    *p2 = cuda_home + "/targets/x86_64-linux/lib/libnvrtc.so.12";
+}
+
+// NVRTC's version WITHOUT loading it: the real file behind the soname is libnvrtc.so.<major>.<minor>.<patch>.  Loading the
+// library costs ~90 ms (measured: the whole of a first plan creation that hits the cubin cache), and a cache hit needs
+// nothing else from it.  False when the name does not parse (then the caller loads the library and asks it).
+bool nvrtc_version_from_filename(int* major, int* minor) {
+    std::string c[2];
+    nvrtc_path_candidates(&c[0], &c[1]);
+    for (const std::string& p : c) {
+        char buf[4096];
+        if (!realpath(p.c_str(), buf)) continue;
+        const std::string real(buf);
+        const size_t at = real.rfind("libnvrtc.so.");
+        int a = 0, b = 0;
+        if (at != std::string::npos && std::sscanf(real.c_str() + at, "libnvrtc.so.%d.%d", &a, &b) == 2 && a >= 11) {
+            *major = a; *minor = b;
+            return true;
+        }
+        return false;                                        // this is the file that would be loaded, and its name says nothing
+    }
+    return false;
+}
+
 NvrtcState& nvrtc_state() {
     static NvrtcState st;
     static std::once_flag once;
@@ -93,8 +121,8 @@ NvrtcState& nvrtc_state() {
         // Prefer the toolkit's NVRTC by path: a process that imported PyTorch already holds torch's bundled
         // libnvrtc.so.12 (CUDA 12.8), which a bare soname lookup would return and whose ptxas predates
         // 256-bit vector stores.
-        std::string cuda_home = std::getenv("CUDA_HOME") ? std::getenv("CUDA_HOME") : "/usr/local/cuda";
-        std::string p1 = cuda_home + "/lib64/libnvrtc.so.12", p2 = cuda_home + "/targets/x86_64-linux/lib/libnvrtc.so.12";
+        std::string p1, p2;
+        nvrtc_path_candidates(&p1, &p2);
         const char* names[] = {p1.c_str(), p2.c_str(), "libnvrtc.so.12", "libnvrtc.so", nullptr};
         std::string tried;
         void* h = open_first(names, &tried);
@@ -244,7 +272,6 @@ void write_file_atomic(const std::string& dir, const std::string& path, const st
 }  // namespace
 
 std::vector<char> nvrtc_compile(const std::string& source, const std::string& name, std::string* log) {
-    const NvrtcApi& n = nvrtc();
     struct H { const char* name; const char* b; const char* e; };
     const H hs[] = {
         {"sde_sim_kernel.cuh", sde_blob_sim_kernel_cuh_begin, sde_blob_sim_kernel_cuh_end},
@@ -256,13 +283,15 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
         {"sde_icdf_tables.cuh", sde_blob_icdf_tables_cuh_begin, sde_blob_icdf_tables_cuh_end},
         {"sde_expr_helpers.cuh", sde_blob_expr_helpers_cuh_begin, sde_blob_expr_helpers_cuh_end},
     };
-    NvrtcState& nst = nvrtc_state();
+    // The cache key covers the NVRTC version — read from the library's file name, so that a cache hit never loads NVRTC
+    int vmaj = 0, vmin = 0;
+    if (!nvrtc_version_from_filename(&vmaj, &vmin)) { NvrtcState& q = nvrtc_state(); vmaj = q.major; vmin = q.minor; }
     // st.global.v4.f64 (256-bit) needs the CUDA 12.9 ptxas; older NVRTC falls back to two 128-bit stores
-    const bool st256 = nst.major > 12 || (nst.major == 12 && nst.minor >= 9);
+    const bool st256_key = vmaj > 12 || (vmaj == 12 && vmin >= 9);
 
     uint64_t key = fnv1a(source.data(), source.size());
     for (const H& h : hs) key = fnv1a(h.b, (size_t)(h.e - h.b), key);
-    const int ver[3] = {nst.major, nst.minor, st256 ? 1 : 0};
+    const int ver[3] = {vmaj, vmin, st256_key ? 1 : 0};
     key = fnv1a(ver, sizeof ver, key);
     {
         std::lock_guard<std::mutex> lock(g_cache_mu);
@@ -283,6 +312,9 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
         }
     }
 
+    const NvrtcApi& n = nvrtc();                             // a miss: now the compiler is needed
+    NvrtcState& nst = nvrtc_state();
+    const bool st256 = nst.major > 12 || (nst.major == 12 && nst.minor >= 9);
     std::vector<std::string> bodies;
     std::vector<const char*> names, ptrs;
     for (const H& h : hs) bodies.emplace_back(h.b, h.e);

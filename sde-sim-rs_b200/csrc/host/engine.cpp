@@ -1,6 +1,9 @@
 // engine.cpp — see engine.h.
 #include "engine.h"
 
+#include <chrono>
+#include <cstdio>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -134,18 +137,37 @@ struct SdeParamsHost {   // must mirror SdeParams in csrc/kernels/sde_sim_kernel
 bool uses_sobol(int rng) { return rng == RNG_SOBOL_CP || rng == RNG_SOBOL_XOR || rng == RNG_SOBOL_RAW; }
 }  // namespace
 
+namespace {
+// SDE_B200_TRACE=1: phase times of plan creation on stderr (lowering, cubin, module load, tables)
+struct PhaseTrace {
+    bool on = std::getenv("SDE_B200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[sde_b200] plan: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
+    PhaseTrace trace;
     low_ = lower_model(u_, opt_.lower);
+    trace.mark("lowering");
     const int S = u_.T() - 1, K = u_.K();
     const size_t dims = (size_t)S * K;
     if (uses_sobol(opt_.lower.rng) && dims > kMaxSobolDims)
         throw ExprError{"sobol needs (T-1)*K = " + std::to_string(dims) + " dimensions; the Joe-Kuo table has 21201 (src/rng/sobol.rs:16)"};
     use_device(opt_.device);
     const DriverApi& d = driver();
+    trace.mark("device context");
     std::string log;
     std::vector<char> cubin = nvrtc_compile(low_.source, "sde_plan.cu", &log);
     prelowered_ = log.rfind("(cached on disk", 0) == 0;       // the cubin shipped in the ahead-of-time cache (build/jit_cache)
+    trace.mark(prelowered_ ? "cubin (disk cache)" : "cubin (NVRTC)");
     cu_check(d.cuModuleLoadData(&mod_, cubin.data()), "cuModuleLoadData(plan)");
+    trace.mark("cuModuleLoadData");
     cu_check(d.cuModuleGetFunction(&fn_sim_, mod_, "sde_sim_kernel"), "cuModuleGetFunction(sde_sim_kernel)");
     cu_check(d.cuModuleGetFunction(&fn_fin_, mod_, "sde_moments_finalize"), "cuModuleGetFunction(sde_moments_finalize)");
     if (low_.smem_bytes > 48 * 1024)
@@ -186,6 +208,7 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
         d_lane_.upload(lane.data(), lane.size() * 4);
         if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 4);
     }
+    trace.mark("tables (host build + upload)");
     cu_check(d.cuStreamCreate(&own_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     cu_check(d.cuStreamCreate(&copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
     cu_check(d.cuEventCreate(&ev_a_, CU_EVENT_DEFAULT), "cuEventCreate");

@@ -281,6 +281,8 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
         throw ExprError{"sobol point index exceeds 2^32 (the reference's scenario index is i32, src/sim/mod.rs:47)"};
     if (low_.wide && opt_.lower.out == OUT_PATHS_NTP && ((uintptr_t)d_out & 15u))
         throw ExprError{"full-path output buffer must be 16-byte aligned (128-bit row stores of the tensor-core kernel)"};
+    if (low_.tma && ((uintptr_t)d_out & 15u))
+        throw ExprError{"full-path output buffer must be 16-byte aligned (bulk copies of row segments)"};
     if (low_.direct && ((uintptr_t)d_out & 31u))
         throw ExprError{"full-path output buffer must be 32-byte aligned (256-bit sector stores)"};
     SdeParamsHost prm{};

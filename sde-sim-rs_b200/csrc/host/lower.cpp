@@ -661,7 +661,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
             return icdf + (size_t)S * (4 + nslot_) * 8 + nq * 512 + (size_t)(block / 32) * nq * 16;
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
-        if (eligible && opt.direct != 1) {
+        if (eligible && opt.direct != 1 && opt.direct != 3) {
             // 24 warps per SM (6 per scheduler), measured on B200 (profiles/r2_c2_ab.md): the step loop needs 64-80 registers,
             // and since its FP64 instructions stopped paying for three register-pair operands (sde_uc, FP32-unit seeds)
             // more resident warps pay again: 485 G path-steps/s sustained at 768 threads, 478 at 512, 480 at 1024
@@ -680,6 +680,18 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         }
         if (opt.direct == 2 && !L.resident)
             throw ExprError{"the persistent-warp kernel needs Sobol (xor / none) full-path NTP output, K <= 2 and (T-1)*K*128 B of shared memory"};
+    }
+    // Opt-in (direct = 3): full paths of a model with an even number of processes (every row segment is 16-byte aligned)
+    // staged per lane in shared memory and handed to the copy engine once per tile (SDE_TMA, sde_sim_kernel.cuh).  The
+    // scattered 256-bit sector stores cost ~26 load/store data-pipe wavefronts per warp instruction (C3: the kernel is 12 %
+    // slower with the stores than without, HBM at 35 %), the staged form 8 — but cp.async.bulk takes uniform-register
+    // addresses, so per-lane segments serialise into a 32-trip loop of ~10 instructions per warp and tile: C3 26.9 ms
+    // against 25.4 ms with sector stores on the same box.  Not selected automatically.
+    {
+        const bool tma_ok = opt.out == OUT_PATHS_NTP && !opt.f32 && (P % 2) == 0 && !L.resident && !gen.matrix;
+        if (opt.direct == 3 && !tma_ok)
+            throw ExprError{"bulk-copy stores need [N][T][P] f64 paths of a model with an even number of processes"};
+        if (tma_ok && opt.direct == 3) { L.tma = true; L.direct = false; }
     }
     // Wide linear model reduced to terminal values / moments under the XOR digital shift: the correlation product runs
     // on the FP64 tensor path (sde_sim_wide.cuh).  A lane keeps 8 wide_mt paths x (2 NB state + NKK draw) doubles in
@@ -716,6 +728,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     if (tt <= 0) {
         tt = 32;
         if (opt.out == OUT_PATHS_NTP && !L.direct) tt = std::max(1, 32 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
+        if (L.tma) tt = std::max(tt, 16);                                      // bulk copies of >= 256 bytes per lane and tile
         if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
     }
     tt = std::max(L.unr, (tt / L.unr) * L.unr);
@@ -734,7 +747,8 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
-        size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * (size_t)((tt * P) | 1) * (opt.f32 ? 4 : 8) : 0;
+        const size_t tile_ld = L.tma ? (size_t)((((tt * P) + 3) & ~3) + 2) : (size_t)((tt * P) | 1);   // SDE_TILE_LD
+        size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * tile_ld * (opt.f32 ? 4 : 8) : 0;
         tile = (tile + 7) & ~(size_t)7;
         size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
@@ -808,6 +822,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         s << "#define SDE_RES_GRP 4\n";                      // steps per unrolled group: one sector store per lane and process
     }
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
+    if (L.tma) s << "#define SDE_TMA 1\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
     if (K > 0 && std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; })) {

@@ -28,7 +28,8 @@ struct LowerOptions {
     int tile_steps = 0;      // 0 = auto
     int min_blocks = 0;      // 0 = auto: CTAs per SM promised to the compiler (__launch_bounds__)
     int direct = -1;         // NTP paths: -1 = auto, 0 = shared-memory transpose, 1 = direct sector stores (tiled kernel),
-                             // 2 = persistent-warp kernel with resident tables (sde_sim_resident.cuh)
+                             // 2 = persistent-warp kernel with resident tables (sde_sim_resident.cuh),
+                             // 3 = per-lane bulk copies shared -> global (cp.async.bulk; tiled kernel, f64, P even)
     int wide_mma = -1;       // wide linear models, terminal / moments: -1 = auto, 0 = time-tiled kernel, 1 = require the
                              // FP64 tensor-core kernel (sde_sim_wide.cuh)
 };
@@ -42,6 +43,7 @@ struct Lowered {
     int unr = 1;             // steps unrolled per loop trip (multiple of ch)
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
     bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
+    bool tma = false;        // NTP full paths leave as per-lane bulk copies from a shared-memory staging row (16-byte aligned buffer)
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory
     bool wide = false;       // tensor-core kernel for wide linear models (sde_sim_wide.cuh): persistent warps, 8 wide_mt paths per warp

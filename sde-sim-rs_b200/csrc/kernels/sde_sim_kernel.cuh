@@ -27,6 +27,14 @@
 //       SDE_TT + 3 steps per tile to absorb the shift.
 //     SDE_DIRECT = 0  (ChaCha-driven modes, wide models): rows are transposed through a per-warp
 //       shared-memory tile and each path's [t0+1, t0+TT] x P segment leaves as contiguous 8-byte-coalesced stores.
+//     SDE_TMA = 1     (f64, P even: every row segment starts and ends on a 16-byte boundary): a lane stages its path's
+//       [t0+1, t0+TT] x P segment in shared memory with 128-bit stores (conflict free: leading dimension = 2 mod 4
+//       doubles) and hands it to the copy engine once per tile — cp.async.bulk shared -> global, one instruction per lane
+//       and tile.  The store bytes never pass the load/store data pipe as scattered sectors: a 256-bit sector store of 32
+//       rows costs ~26 data-pipe wavefronts (measured, profiles/r2_ncu_full_c3_summary.txt), the same 1 KB staged with
+//       128-bit shared stores 8, and the pipe is shared with the inverse normal's table reads.  Opt-in (ntp_direct = 4):
+//       the bulk copy takes uniform-register addresses, so the 32 lanes' copies serialise (~10 instructions each) and the
+//       net effect on C3 is -6 %; a 2-D tensor-map store per warp would avoid that (not built).
 //
 // Macros expected from the generated prelude:
 //   SDE_P, SDE_K, SDE_KK           processes / stochastic factors / max(K, 1)
@@ -65,13 +73,21 @@
 #ifndef SDE_DIRECT
 #define SDE_DIRECT 0
 #endif
+#ifndef SDE_TMA
+#define SDE_TMA 0
+#endif
 #ifndef SDE_ST256
 #define SDE_ST256 1   /* 256-bit st.global.v4.f64 (PTX ISA 8.8 / CUDA 12.9 ptxas) */
 #endif
 // steps staged per tile buffer: the direct path lets a warp run up to 3 steps past the tile boundary
 #define SDE_TS (SDE_TT + (SDE_DIRECT ? 3 : 0))
-// leading dimension of a warp's staging row: odd => conflict-free column writes
+// leading dimension of a warp's staging row: odd => conflict-free column writes; bulk-copy mode: = 2 (mod 4) doubles =>
+// 16-byte aligned rows whose 128-bit writes are conflict free (8 lanes x 16 B per wavefront land in 8 distinct bank groups)
+#if SDE_TMA
+#define SDE_TILE_LD ((((SDE_TT * SDE_P) + 3) & ~3) + 2)
+#else
 #define SDE_TILE_LD ((SDE_TT * SDE_P) | 1)
+#endif
 #define SDE_STEP_LD (4 + SDE_NSLOT)
 
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
@@ -276,6 +292,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     sde_real* my_tile = s_tile + (size_t)(warp * 32 + lane) * SDE_TILE_LD;
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
     const long long s_warp0 = s_local - lane;
+    (void)valid_mask; (void)s_warp0;
 #endif
 #elif SDE_OUT == 1
     if (valid) {
@@ -424,7 +441,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         auto advance = [&](const int t, const sde_real (&zu)[SDE_KK], const sde_u0_t u0) __attribute__((always_inline)) {
             const int tl = t - t0;
             sde_model_step(row, cache, ct, zu, u0, s_step + tl * SDE_STEP_LD);
-#if SDE_OUT == 0 && !SDE_DIRECT
+#if SDE_OUT == 0 && !SDE_DIRECT && !SDE_TMA
 #pragma unroll
             for (int p = 0; p < SDE_P; ++p) my_tile[tl * SDE_P + p] = row[p];
 #elif SDE_OUT == 1
@@ -474,6 +491,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
                 }
             }
+#elif SDE_OUT == 0 && SDE_TMA
+            sde_real vals[SDE_UNR * SDE_P];                     // rows tc+1 .. tc+UNR, in output order
+#pragma unroll
+            for (int j = 0; j < SDE_UNR; ++j) {
+                advance(tc + j, zu[j], u0[j]);
+#pragma unroll
+                for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
+            }
+            // the copy engine may still be reading the previous tile's segment from this row: its read is waited for here,
+            // a whole group's draws and updates after it was issued (no-op from the second group of a tile on)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            {
+                double2* dst = reinterpret_cast<double2*>(my_tile + (tc - t0) * SDE_P);
+#pragma unroll
+                for (int q = 0; q < SDE_UNR * SDE_P / 2; ++q) dst[q] = make_double2(vals[2 * q], vals[2 * q + 1]);
+            }
 #else
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
@@ -491,6 +524,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) my_row[(size_t)(t + 1) * SDE_P + p] = row[p];
             }
+#elif SDE_OUT == 0 && SDE_TMA
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+            for (int p = 0; p < SDE_P; ++p) my_tile[(t - t0) * SDE_P + p] = row[p];
 #endif
         };
 
@@ -553,7 +590,16 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
         if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
 
-#if SDE_OUT == 0 && !SDE_DIRECT
+#if SDE_OUT == 0 && SDE_TMA
+        // hand this lane's [t0+1, t_end] x P segment (contiguous in HBM, 16-byte aligned: P is even) to the copy engine
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the lane's own generic-proxy writes -> async proxy
+        if (valid) {
+            const sde_real* src_g = out_r + ((size_t)s_local * T + (t0 + 1)) * SDE_P;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(src_g), "r"((unsigned)__cvta_generic_to_shared(my_tile)), "r"((unsigned)((t_end - t0) * SDE_P * 8)) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#elif SDE_OUT == 0 && !SDE_DIRECT
         // transpose through shared memory: each path's [t0+1, t_end] x P segment is contiguous in HBM
         __syncwarp();
         {
@@ -605,6 +651,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         __syncthreads();                                      // next tile's staged data visible; this tile's buffer free
 #endif
     }
+#if SDE_OUT == 0 && SDE_TMA
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // the last segment has left shared memory and reached global memory
+#endif
 
 #if SDE_OUT == 2
     if (valid) {

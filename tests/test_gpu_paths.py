@@ -237,6 +237,21 @@ def test_persistent_kernel_many_items_per_warp_matches_tiled(scramble, mode):
             assert rel_err(outs[1][ok], outs[0][ok]) <= 1e-12
 
 
+@pytest.mark.parametrize("rng_method,scramble,scheme,steps,N", [("sobol", "xor", "runge-kutta", 1000, 600), ("pseudo", "cp_shift_per_path", "euler", 37, 300),
+                                                            ("sobol", "cp_shift_per_path", "euler", 50, 257)])
+def test_bulk_copy_store_path_is_bit_identical(rng_method, scramble, scheme, steps, N):
+    # ntp_direct=4: rows staged per lane in shared memory and written by cp.async.bulk (P even); same values as the default path
+    times, init = grid(1000, steps), {"S": 100.0, "v": 0.04}
+    kw = dict(scramble=scramble, seed=9, scenario_offset=3)
+    a = S.Plan(S.Universe(HESTON_EQ, times), scheme, rng_method, scramble=scramble, ntp_direct=4)
+    assert "#define SDE_TMA 1" in a.source
+    got = a.run(init, N, seed=9, scenario_offset=3).cpu().numpy()
+    ref = S.simulate(HESTON_EQ, times, N, init, rng_method, scheme, **kw).to_numpy()
+    assert np.array_equal(got, ref)
+    with pytest.raises(ValueError, match="even number of processes"):
+        S.Plan(S.Universe(GBM_EQ, times), "euler", "pseudo", ntp_direct=4)
+
+
 def test_direct_store_needs_aligned_output():
     plan = S.Plan(S.Universe(GBM_EQ, grid(252, 8)), "euler", "sobol", scramble="xor")
     buf = torch.empty(100 * 9 + 1, dtype=torch.float64, device="cuda")

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cstdlib>
+#include <string>
 
 constexpr int T = 253;
 
@@ -94,12 +96,55 @@ __global__ void __launch_bounds__(1024, 1) k_line4(double* out, long long n_rows
     }
 }
 
-int main() {
+// usage: store_patterns                      the bandwidth table (all patterns x threads per SM)
+//        store_patterns <pattern> <threads> <seconds>   one pattern in a loop for power sampling (nvidia-smi alongside):
+//        patterns: A D2 D4 D8 B C S   (S = sequential: consecutive warps write consecutive 1 KB pieces)
+__global__ void __launch_bounds__(1024, 1) k_seq(double* out, long long n_rows, int dummy) {
+    const long long total4 = n_rows * T / 4;                              // 32-byte pieces
+    double v = (double)threadIdx.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        v += 1.0;
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * i), "d"(v), "d"(v), "d"(v), "d"(v) : "memory");
+    }
+}
+
+int main(int argc, char** argv) {
     const long long n_rows = 1ll << 24;
     double* out;
     if (cudaMalloc(&out, (size_t)n_rows * T * 8 + 4096) != cudaSuccess) { printf("alloc failed\n"); return 1; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (argc >= 4) {
+        const std::string pat = argv[1];
+        const int threads = atoi(argv[2]);
+        const double seconds = atof(argv[3]);
+        double bytes = 0;
+        auto launch = [&] {
+            if (pat == "A") { k_sector<<<148, threads>>>(out, n_rows, 0); bytes = (double)n_rows * 62 * 32; }
+            else if (pat == "D2") { k_sector_burst<2><<<148, threads>>>(out, n_rows, 0); bytes = (double)n_rows * 31 * 64; }
+            else if (pat == "D4") { k_sector_burst<4><<<148, threads>>>(out, n_rows, 0); bytes = (double)n_rows * 15 * 128; }
+            else if (pat == "D8") { k_sector_burst<8><<<148, threads>>>(out, n_rows, 0); bytes = (double)n_rows * 7 * 256; }
+            else if (pat == "C") { k_line4<<<148, threads>>>(out, n_rows, 0); bytes = (double)n_rows * 14 * 128; }
+            else if (pat == "S") { k_seq<<<148, threads>>>(out, n_rows, 0); bytes = (double)(n_rows * T / 4) * 32; }
+            else if (pat == "B") {
+                cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, threads * 288 + 128);
+                k_tma<<<148, threads, threads * 288 + 128>>>(out, n_rows, 0); bytes = (double)n_rows * 14 * 128;
+            }
+        };
+        launch(); launch();
+        cudaDeviceSynchronize();
+        float ms1;
+        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms1, e0, e1);
+        const int n = (int)(seconds * 1e3 / ms1) + 1;
+        cudaEventRecord(e0);
+        for (int i = 0; i < n; ++i) launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%s threads %d: %d launches, %.3f ms each, %.0f GB/s (%s)\n", pat.c_str(), threads, n, ms / n, bytes / (ms / n) * 1e-6,
+               cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     auto run = [&](const char* name, auto launch, double bytes) {
         launch(); launch();
         cudaEventRecord(e0);

@@ -310,7 +310,8 @@ def _cached_plan(equations, time_steps, scheme, rng_method, **kw) -> Plan:
     return plan
 
 
-_EXTENSIONS = ("seed", "output", "layout", "scramble", "icdf", "arithmetic", "rk_variant", "device", "scenario_offset", "dtype", "generator")
+_EXTENSIONS = ("seed", "output", "layout", "scramble", "icdf", "arithmetic", "rk_variant", "compat", "device", "devices", "scenario_offset",
+               "dtype", "generator")
 
 
 def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], scenarios: int,
@@ -327,8 +328,11 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
     behaviour) | xor | none, `icdf` reference|fast|single, `arithmetic` strict|fast, `rk_variant` reference|textbook,
     `device`, `scenario_offset`, `dtype` f64|f32 (f32: state, arithmetic and stored values in single precision; needs
     arithmetic="fast"), `generator` chacha8 (the reference's stream, bit-exact) | philox (Philox4x32-10: a cheaper
-    counter-based stream for rng_method != "sobol"; agrees with the reference statistically, not draw for draw).  With any of them the result is a `Filtration` (the dense value tensor, resident on the GPU) unless
-    frame=True; frame=False always returns the `Filtration`.
+    counter-based stream for rng_method != "sobol"; agrees with the reference statistically, not draw for draw),
+    `compat` (SURVEY's name for `rk_variant`: "reference" | "textbook"), `devices` (a list of GPU ordinals, or "all": the
+    scenarios are sharded over them inside one C call like rayon's par_iter, see `simulate_devices` — the result is then the
+    list of per-device `Filtration` shards, or one `Filtration` of merged moments).  With any of them the result is a
+    `Filtration` (the dense value tensor, resident on the GPU) unless frame=True; frame=False always returns the `Filtration`.
     """
     unknown = [k for k in ext if k not in _EXTENSIONS]
     if unknown:
@@ -336,6 +340,30 @@ def simulate(processes_equations: Sequence[str], time_steps: Sequence[float], sc
     if frame not in (True, False, "auto"):
         raise ValueError("frame must be True, False or 'auto'")
     want_frame = (len(ext) == 0) if frame == "auto" else bool(frame)
+    if "compat" in ext:
+        compat = ext.pop("compat")
+        if "rk_variant" in ext and ext["rk_variant"] != compat:
+            raise ValueError("compat and rk_variant name the same option and disagree")
+        ext["rk_variant"] = compat
+    if ext.get("devices") is not None:
+        devices = ext.pop("devices")
+        if ext.pop("device", None) is not None:
+            raise ValueError("give either device or devices")
+        if ext.pop("scenario_offset", 0):
+            raise ValueError("scenario_offset is per shard when devices is given")
+        shards = simulate_devices(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme,
+                                  devices=None if devices == "all" else devices, **ext)
+        if not want_frame:
+            return shards
+        if isinstance(shards, Filtration):
+            raise ValueError("frame=True needs output='paths' (the reference's frame holds every row)")
+        try:
+            import polars as pl
+            return pl.concat([f.to_polars() for f in shards])
+        except ImportError:
+            import pandas as pd
+            return pd.concat([f.to_pandas() for f in shards], ignore_index=True)
+    ext.pop("devices", None)
     res = _simulate_filtration(processes_equations, time_steps, scenarios, initial_values, rng_method, scheme, **ext)
     if not want_frame:
         return res

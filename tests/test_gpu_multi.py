@@ -80,3 +80,34 @@ def test_nccl_moment_merge_on_real_devices():
         assert m[0, 0] == N and abs(m[0, 1] / whole.mean() - 1) <= 1e-13 and abs(m[0, 2] / ((whole - whole.mean()) ** 2).sum() - 1) <= 1e-10
     paths = S.DevicePlans(S.Universe(GBM_EQ, times), "euler", "pseudo", devices=devs, output="terminal", **kw).run({"X1": 1.0}, N, seed=42)
     assert np.array_equal(np.concatenate([p.cpu().numpy() for p in paths])[:, 0], whole)
+
+
+def test_simulate_keywords_devices_and_compat():
+    """SURVEY §8(b)'s keyword-only extras on the drop-in call itself: `devices` shards the scenarios over GPUs inside one C
+    call (rayon's par_iter, src/sim/mod.rs:41-43), `compat` is the survey's name for rk_variant."""
+    import sde_sim_rs as S
+    from conftest import GBM_EQ, grid
+
+    times, init, N = grid(252, 24), {"X1": 1.0}, 1001
+    one = S.simulate(GBM_EQ, times, N, init, "sobol", "euler", seed=3, scramble="xor")
+    devs = [0, 0, 0] if torch.cuda.device_count() < 2 else list(range(torch.cuda.device_count()))
+    shards = S.simulate(GBM_EQ, times, N, init, "sobol", "euler", seed=3, scramble="xor", devices=devs)
+    assert isinstance(shards, list) and len(shards) == len(devs)
+    got = np.concatenate([f.to_numpy() for f in shards], axis=0)
+    assert np.array_equal(got, one.to_numpy())                 # union of the shards: bit-identical
+    fr = S.simulate(GBM_EQ, times, 60, init, "sobol", "euler", seed=3, scramble="xor", devices=devs, frame=True)
+    ref = S.simulate(GBM_EQ, times, 60, init, "sobol", "euler", seed=3, scramble="xor", frame=True)
+    assert list(fr.columns) == list(ref.columns) and len(fr) == len(ref)
+    assert np.array_equal(np.asarray(fr["value"]), np.asarray(ref["value"])) and np.array_equal(np.asarray(fr["scenario"]), np.asarray(ref["scenario"]))
+    mom = S.simulate(GBM_EQ, times, N, init, "pseudo", "euler", seed=3, output="moments", devices="all")
+    full = S.simulate(GBM_EQ, times, N, init, "pseudo", "euler", seed=3, output="terminal").to_numpy()[:, 0]
+    m = mom.to_numpy()
+    assert m[0, 0] == N and abs(m[0, 1] / full.mean() - 1) < 1e-13
+    a = S.simulate(GBM_EQ, times, 50, init, "pseudo", "runge-kutta", seed=5, compat="textbook").to_numpy()
+    b = S.simulate(GBM_EQ, times, 50, init, "pseudo", "runge-kutta", seed=5, rk_variant="textbook").to_numpy()
+    c = S.simulate(GBM_EQ, times, 50, init, "pseudo", "runge-kutta", seed=5).to_numpy()
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    with pytest.raises(ValueError, match="disagree"):
+        S.simulate(GBM_EQ, times, 5, init, "pseudo", "runge-kutta", compat="textbook", rk_variant="reference")
+    with pytest.raises(TypeError, match="unexpected keyword"):
+        S.simulate(GBM_EQ, times, 5, init, "pseudo", "euler", device_list=[0])

@@ -94,6 +94,21 @@ def test_factored_lowering_with_poisson_terms(oracle, scheme):
     assert (np.abs(ref[:, -1, 0] - init["X"]) > 0.05).mean() > 0.3        # the jumps are really there
 
 
+@pytest.mark.parametrize("name,eqs,init,wiener", [MODELS[0], MODELS[5], MODELS[6]], ids=[MODELS[0][0], MODELS[5][0], MODELS[6][0]])
+def test_factored_lowering_textbook_runge_kutta(oracle, name, eqs, init, wiener):
+    """rk_variant="textbook" (k1 at the settled row, the separately named non-compat mode) through the same factored form."""
+    times, N = grid(252, 48), 200
+    U = oracle.Universe(eqs, times)
+    inj = _inject(oracle, U, N, 13, wiener)
+    ref = oracle.simulate(U, init, N, "runge-kutta", inject=inj, textbook_rk=True)
+    dev = torch.from_numpy(inj).cuda()
+    fast = S.Plan(S.Universe(eqs, times), "runge-kutta", "pseudo", inject=dev, arithmetic="fast", rk_variant="textbook").run(init, N).cpu().numpy()
+    compat = S.Plan(S.Universe(eqs, times), "runge-kutta", "pseudo", inject=dev, arithmetic="fast").run(init, N).cpu().numpy()
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=(0, 1), keepdims=True) * 1e-3)
+    assert np.max(np.abs(fast - ref) / scale) <= 1e-12
+    assert np.max(np.abs(compat - ref) / scale) > 1e-9                    # the reference's stale-cache variant is a different scheme
+
+
 def test_generated_source_shows_the_grouping():
     """What the pass did is readable in the plan's source (sde_plan_source): one root per stage, the two Wiener terms of X
     that share sqrt(Y+) X merged into one weight, X taken out of the drift + diffusion sum."""

@@ -744,6 +744,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     }
     L.tt = tt;
     const int ts = tt + (L.direct ? 3 : 0);                  // SDE_TS
+    int nstage = 2;                                          // SDE_NSTAGE: stage buffers of the tile hand-over (see sde_sim_kernel.cuh)
     auto smem_for = [&](int block) {   // mirrors the SDE_SMEM_* macros of sde_sim_kernel.cuh
         const int nw = block / 32;
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
@@ -752,9 +753,21 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         tile = (tile + 7) & ~(size_t)7;
         size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
-        return icdf + tile + 2 * stage + mom;
+        return icdf + tile + (size_t)nstage * stage + mom + (nstage == 4 ? 16 : 0);
     };
     if (opt.block <= 0 && !L.direct) while (L.block > 32 && smem_for(L.block) > 200 * 1024) L.block /= 2;
+    {
+        // four stage buffers + mbarrier hand-over (a tile of slack between the warps of a CTA) where they are cheap: the
+        // staged tables of four tiles within a quarter of the CTA's shared memory and the CTA still at <= 100 KB
+        nstage = 4;
+        const size_t with4 = smem_for(L.block);
+        nstage = 2;
+        const size_t with2 = smem_for(L.block);
+        bool use4 = u.T() - 1 > 2 * tt && with4 <= 100 * 1024 && (with4 - with2) * 2 <= with4;
+        if (const char* g = std::getenv("SDE_B200_NSTAGE")) use4 = std::atoi(g) == 4 && with4 <= 200 * 1024;   // tuning
+        nstage = use4 ? 4 : 2;
+    }
+    L.nstage = nstage;
     L.smem_bytes = smem_for(L.block);
     if (L.smem_bytes > 227 * 1024) throw ExprError{"model too large for the shared-memory staging tile (P = " + std::to_string(P) + ")"};
     {
@@ -823,6 +836,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     }
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
     if (L.tma) s << "#define SDE_TMA 1\n";
+    if (!L.wide && !L.resident && L.nstage == 4) s << "#define SDE_NSTAGE 4\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";
     if (K > 0 && std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; })) {

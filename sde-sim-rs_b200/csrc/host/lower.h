@@ -43,6 +43,7 @@ struct Lowered {
     int unr = 1;             // steps unrolled per loop trip (multiple of ch)
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
     bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
+    int nstage = 2;          // time-tiled kernel: stage buffers (2: __syncthreads per tile; 4: mbarrier hand-over, SDE_NSTAGE)
     bool tma = false;        // NTP full paths leave as per-lane bulk copies from a shared-memory staging row (16-byte aligned buffer)
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory

@@ -99,7 +99,18 @@
 #define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * 32 * 4) : 0)
 #define SDE_SMEM_STAGE_BYTES (SDE_SMEM_STEP_BYTES + SDE_SMEM_BW_BYTES + SDE_SMEM_LANE_BYTES)
 #define SDE_SMEM_MOM_BYTES ((SDE_OUT == 3) ? (SDE_NW * 3 * 8) : 0)
-#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + 2 * SDE_SMEM_STAGE_BYTES + SDE_SMEM_MOM_BYTES)
+// SDE_NSTAGE stage buffers.  2: tile k+1 is committed at the end of tile k, one __syncthreads per tile.  4: tile k+2 is
+// committed at the end of tile k and announced on an mbarrier that a warp only waits for at the start of tile k+2 — a whole
+// tile of slack, so warps whose store phases drift no longer wait for each other every tile (the barrier stall was 7 % of
+// C3's issue slots with the row stores on, 2 % without; profiles/r2_ncu_full_c3_summary.txt).  Buffer (k+2) % 4 was last
+// read in tile k-2, which every warp has left: a warp reaches the end of tile k only after the phase of tile k completed,
+// i.e. after every warp arrived at the end of tile k-2.  Two mbarriers (even / odd tiles) keep a waiting warp at most one
+// phase behind its barrier.
+#ifndef SDE_NSTAGE
+#define SDE_NSTAGE 2
+#endif
+#define SDE_SMEM_MBAR_BYTES (SDE_NSTAGE == 4 ? 16 : 0)
+#define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES + SDE_NSTAGE * SDE_SMEM_STAGE_BYTES + SDE_SMEM_MOM_BYTES + SDE_SMEM_MBAR_BYTES)
 
 // prefetch register counts (compile-time): entries of each staged table owned by one thread
 #define SDE_PF_BW ((SDE_TS * SDE_KK * SDE_NW + SDE_BLOCK - 1) / SDE_BLOCK)
@@ -149,7 +160,10 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     double* s_icdf = reinterpret_cast<double*>(smem);
     sde_real* s_tile = reinterpret_cast<sde_real*>(smem + SDE_SMEM_ICDF_BYTES);
     unsigned char* s_stage = smem + SDE_SMEM_ICDF_BYTES + SDE_SMEM_TILE_BYTES;     // two buffers of SDE_SMEM_STAGE_BYTES
-    double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_BYTES - SDE_SMEM_MOM_BYTES);
+    double* s_mom = reinterpret_cast<double*>(smem + SDE_SMEM_BYTES - SDE_SMEM_MBAR_BYTES - SDE_SMEM_MOM_BYTES);
+#if SDE_NSTAGE == 4
+    const unsigned s_mbar = (unsigned)__cvta_generic_to_shared(smem + SDE_SMEM_BYTES - SDE_SMEM_MBAR_BYTES);   // two 8-byte mbarriers
+#endif
     (void)s_icdf; (void)s_tile; (void)s_mom;
     sde_real* const out_r = reinterpret_cast<sde_real*>(prm.out);   // rows are sde_real (f32 plans: float)
     (void)out_r;
@@ -301,10 +315,17 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     }
 #endif
 
-    {   // tile 0 is staged synchronously
+    {   // tile 0 (and tile 1 with four stage buffers) is staged synchronously
         SdeTilePrefetch pf;
         issue(0, pf);
         commit(0, pf, 0);
+#if SDE_NSTAGE == 4
+        if (SDE_TT < S) { issue(SDE_TT, pf); commit(SDE_TT, pf, 1); }
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_mbar), "r"(SDE_BLOCK) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_mbar + 8u), "r"(SDE_BLOCK) : "memory");
+        }
+#endif
     }
     __syncthreads();
 
@@ -313,7 +334,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     int tail_t = -1;
 #endif
     int buf = 0;
+#if SDE_NSTAGE == 4
+    int tile = 0;
+    for (int t0 = 0; t0 < S; t0 += SDE_TT, buf = (buf + 1) & 3, ++tile) {
+        if (tile >= 2) {
+            // tile `tile` was committed by every thread at the end of tile - 2: wait for that phase (parity of its count on
+            // the even / odd barrier)
+            const unsigned bar = s_mbar + 8u * (unsigned)(tile & 1), parity = (unsigned)(((tile - 2) >> 1) & 1);
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            } while (!done);
+        }
+#else
     for (int t0 = 0; t0 < S; t0 += SDE_TT, buf ^= 1) {
+#endif
         const int t_end = min(t0 + SDE_TT, S);
         const double* s_step = reinterpret_cast<const double*>(s_stage + buf * SDE_SMEM_STAGE_BYTES);
         const sde_u32* s_bw = reinterpret_cast<const sde_u32*>(s_stage + buf * SDE_SMEM_STAGE_BYTES + SDE_SMEM_STEP_BYTES);
@@ -531,7 +567,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
         };
 
+#if SDE_NSTAGE == 4
+        const bool more = t0 + 2 * SDE_TT < S;                // a tile after the next follows: prefetch it behind the last group
+        const int t0_next = t0 + 2 * SDE_TT;
+#else
         const bool more = t0 + SDE_TT < S;                    // another tile follows: prefetch it behind the last group
+        const int t0_next = t0 + SDE_TT;
+#endif
         SdeTilePrefetch pf;
 #if SDE_DIRECT
         {
@@ -549,7 +591,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             const int n_groups = t_hi > tc ? (t_hi - tc) >> 2 : 0;
 #pragma unroll 1
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += 4) group(tc);
-            if (more) issue(t0 + SDE_TT, pf);
+            if (more) issue(t0_next, pf);
             if (n_groups > 0) { group(tc); tc += 4; }
             // The <= 3 steps after the last full group run as soon as the groups are done, in the tile whose staged tables
             // [t0, t0 + SDE_TS) hold them.  (The last group can end up to 3 steps before a tile boundary; left to the last
@@ -573,14 +615,14 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             // `no_instruction` was the second largest stall)
 #pragma unroll 1
             for (int gi = 0; gi < n_groups; ++gi, tc += SDE_UNR) {
-                if (more && gi + 1 == n_groups) issue(t0 + SDE_TT, pf);
+                if (more && gi + 1 == n_groups) issue(t0_next, pf);
                 group(tc);
             }
-            if (more && n_groups == 0) issue(t0 + SDE_TT, pf);
+            if (more && n_groups == 0) issue(t0_next, pf);
 #else
 #pragma unroll 1
             for (int gi = 0; gi + 1 < n_groups; ++gi, tc += SDE_UNR) group(tc);
-            if (more) issue(t0 + SDE_TT, pf);
+            if (more) issue(t0_next, pf);
             if (n_groups > 0) { group(tc); tc += SDE_UNR; }
 #pragma unroll
             for (int j = 0; j < SDE_UNR - 1; ++j)
@@ -588,7 +630,14 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
         }
 #endif
-        if (more) commit(t0 + SDE_TT, pf, buf ^ 1);           // the other buffer was last read in tile k-1 (barrier below)
+#if SDE_NSTAGE == 4
+        if (more) {
+            commit(t0_next, pf, (buf + 2) & 3);               // last read in tile k-2, which every warp has left (see SDE_NSTAGE)
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(s_mbar + 8u * (unsigned)(tile & 1)) : "memory");
+        }
+#else
+        if (more) commit(t0_next, pf, buf ^ 1);               // the other buffer was last read in tile k-1 (barrier below)
+#endif
 
 #if SDE_OUT == 0 && SDE_TMA
         // hand this lane's [t0+1, t_end] x P segment (contiguous in HBM, 16-byte aligned: P is even) to the copy engine
@@ -647,7 +696,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         }
         __syncwarp();
 #endif
-#ifndef SDE_DEBUG_NOBARRIER                                   // (profiling aid: results are garbage without it)
+#if SDE_NSTAGE != 4 && !defined(SDE_DEBUG_NOBARRIER)           // (NOBARRIER: profiling aid, results are garbage)
         __syncthreads();                                      // next tile's staged data visible; this tile's buffer free
 #endif
     }

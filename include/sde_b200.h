@@ -112,7 +112,8 @@ typedef struct sde_options {
     int32_t min_blocks;       /* 0 = auto; CTAs per SM promised to the compiler (tuning)            */
     int32_t ntp_direct;       /* SDE_LAYOUT_NTP paths: 0 = auto; 1 = shared-memory transpose; 2 = direct sector stores from the
                                * time-tiled kernel; 3 = persistent-warp kernel with resident tables (Sobol xor / none only);
-                               * 4 = per-lane bulk copies shared -> global (f64, even number of processes, 16-byte aligned buffer) */
+                               * 4 = per-lane bulk copies shared -> global (f64, even number of processes, 16-byte aligned buffer);
+                               * 5 = per-warp 2-D tensor-map stores (f64, 2 or 4 processes, K <= 2, 16-byte aligned buffer)        */
     int32_t dtype;            /* enum sde_dtype: element type of the state, the model arithmetic and the stored rows.
                                * SDE_DTYPE_F32 needs arith = SDE_ARITH_FAST; paths / terminal buffers are then float,
                                * moments stay [P][3] f64 (accumulated in f64 from the f32 terminal values)                        */

@@ -81,7 +81,7 @@ PlanOptions plan_options(const Universe& u, const char* scheme, const char* rng_
     po.lower.block = o.block_threads;
     po.lower.tile_steps = o.tile_steps;
     po.lower.min_blocks = o.min_blocks;
-    po.lower.direct = o.ntp_direct == 1 ? 0 : (o.ntp_direct == 2 ? 1 : (o.ntp_direct == 3 ? 2 : (o.ntp_direct == 4 ? 3 : -1)));
+    po.lower.direct = o.ntp_direct == 1 ? 0 : (o.ntp_direct == 2 ? 1 : (o.ntp_direct == 3 ? 2 : (o.ntp_direct == 4 ? 3 : (o.ntp_direct == 5 ? 4 : -1))));
     if (o.wide_mma < 0 || o.wide_mma > 2) throw ExprError{"unknown wide_mma mode"};
     po.lower.wide_mma = o.wide_mma == 1 ? 0 : (o.wide_mma == 2 ? 1 : -1);
     (void)u;

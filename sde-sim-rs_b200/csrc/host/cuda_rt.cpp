@@ -69,6 +69,7 @@ DriverState& driver_state() {
         SDE_LOAD(cuOccupancyMaxActiveBlocksPerMultiprocessor)
         SDE_LOAD(cuMemcpyDtoDAsync) SDE_LOAD(cuMemcpyPeerAsync) SDE_LOAD(cuCtxEnablePeerAccess) SDE_LOAD(cuDeviceCanAccessPeer)
 #undef SDE_LOAD
+        st.api.cuTensorMapEncodeTiled = reinterpret_cast<decltype(st.api.cuTensorMapEncodeTiled)>(dlsym(h, "cuTensorMapEncodeTiled"));
         if (missing) { st.why = "CUDA driver is missing symbols: " + miss; return; }
         CUresult r = st.api.cuInit(0);
         if (r != CUDA_SUCCESS) { st.why = "cuInit failed (" + std::to_string((int)r) + "): no usable GPU"; return; }

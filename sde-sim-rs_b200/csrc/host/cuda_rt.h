@@ -55,6 +55,10 @@ struct DriverApi {
     CUresult (*cuMemcpyPeerAsync)(CUdeviceptr, CUcontext, CUdeviceptr, CUcontext, size_t, CUstream);
     CUresult (*cuCtxEnablePeerAccess)(CUcontext, unsigned);
     CUresult (*cuDeviceCanAccessPeer)(int*, CUdevice, CUdevice);
+    // optional (CUDA >= 12.0 drivers): tensor maps for the per-warp 2-D bulk stores of the time-tiled kernel; may be null
+    CUresult (*cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 };
 
 // NCCL, dlopen'ed like the driver (libnccl.so.2: the copy PyTorch already mapped when running under it, else the

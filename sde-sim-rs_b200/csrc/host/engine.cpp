@@ -326,7 +326,22 @@ void Plan::launch(uint64_t n, uint64_t seed, uint64_t scenario_offset, double* d
         if (d_partials_.bytes() < need) { cu_check(d.cuStreamSynchronize(stream), "cuStreamSynchronize"); d_partials_.alloc(need); }
         prm.partials = d_partials_.ptr();
     }
-    void* args[] = {&prm};
+    alignas(64) CUtensorMap tmap;
+    void* args[] = {&prm, &tmap};
+    if (low_.tma2) {
+        // the output as a 2-D tensor [n rows][T P doubles]; a box is 32 rows x 128 bytes, written from shared memory in the
+        // 128-byte swizzle pattern; rows / columns outside the tensor are clipped by the copy engine
+        if (!d.cuTensorMapEncodeTiled) throw ExprError{"this CUDA driver has no cuTensorMapEncodeTiled (needed by ntp_direct=5)"};
+        if (n >= (1ull << 31)) throw ExprError{"tensor-map stores address paths with 32-bit coordinates: at most 2^31 - 1 paths per launch"};
+        const cuuint64_t TP = (cuuint64_t)u_.T() * (cuuint64_t)u_.P();
+        const cuuint64_t dims[2] = {TP, (cuuint64_t)n};
+        const cuuint64_t strides[1] = {TP * 8};
+        const cuuint32_t box[2] = {16, 32};
+        const cuuint32_t estr[2] = {1, 1};
+        cu_check(d.cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+                 "cuTensorMapEncodeTiled");
+    }
     cu_check(d.cuLaunchKernel(fn_sim_, (unsigned)grid, 1, 1, (unsigned)low_.block, 1, 1, (unsigned)low_.smem_bytes, stream, args, nullptr),
              "cuLaunchKernel(sde_sim_kernel)");
     if (n_launches) ++*n_launches;

@@ -661,7 +661,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
             return icdf + (size_t)S * (4 + nslot_) * 8 + nq * 512 + (size_t)(block / 32) * nq * 16;
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
-        if (eligible && opt.direct != 1 && opt.direct != 3) {
+        if (eligible && opt.direct != 1 && opt.direct != 3 && opt.direct != 4) {
             // 24 warps per SM (6 per scheduler), measured on B200 (profiles/r2_c2_ab.md): the step loop needs 64-80 registers,
             // and since its FP64 instructions stopped paying for three register-pair operands (sde_uc, FP32-unit seeds)
             // more resident warps pay again: 485 G path-steps/s sustained at 768 threads, 478 at 512, 480 at 1024
@@ -692,6 +692,11 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         if (opt.direct == 3 && !tma_ok)
             throw ExprError{"bulk-copy stores need [N][T][P] f64 paths of a model with an even number of processes"};
         if (tma_ok && opt.direct == 3) { L.tma = true; L.direct = false; }
+        // direct = 4: one 2-D tensor-map store per warp and 128-byte box row (SDE_TMA == 2): P = 2 or 4, groups of 4 steps
+        const bool tma2_ok = tma_ok && (P == 2 || P == 4) && L.unr == 4;
+        if (opt.direct == 4 && !tma2_ok)
+            throw ExprError{"tensor-map stores need [N][T][P] f64 paths of a model with 2 or 4 processes and K <= 2"};
+        if (tma2_ok && opt.direct == 4) { L.tma = true; L.tma2 = true; L.direct = false; }
     }
     // Wide linear model reduced to terminal values / moments under the XOR digital shift: the correlation product runs
     // on the FP64 tensor path (sde_sim_wide.cuh).  A lane keeps 8 wide_mt paths x (2 NB state + NKK draw) doubles in
@@ -729,6 +734,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         tt = 32;
         if (opt.out == OUT_PATHS_NTP && !L.direct) tt = std::max(1, 32 / P);   // staging tile: 32 paths x (tt*P) doubles per warp
         if (L.tma) tt = std::max(tt, 16);                                      // bulk copies of >= 256 bytes per lane and tile
+        if (L.tma2) tt = 16;                                                   // two 8-step boxes (P = 2) per tile
         if (sobol) tt = std::min(tt, std::max(1, 128 / KK));   // lane-table slice: 2 x tt*K*128 B of shared memory
     }
     tt = std::max(L.unr, (tt / L.unr) * L.unr);
@@ -750,6 +756,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         size_t icdf = (opt.icdf == 1 && opt.rng != RNG_INJECT) ? (size_t)(128 * 2 * 8 + 64) * 8 : 0;   // SDE_ICDF_TABLE_DOUBLES
         const size_t tile_ld = L.tma ? (size_t)((((tt * P) + 3) & ~3) + 2) : (size_t)((tt * P) | 1);   // SDE_TILE_LD
         size_t tile = (opt.out == OUT_PATHS_NTP && !L.direct) ? (size_t)nw * 32 * tile_ld * (opt.f32 ? 4 : 8) : 0;
+        if (L.tma2) { icdf = (icdf + 1023) & ~(size_t)1023; tile = (size_t)nw * 2 * 4096; }
         tile = (tile + 7) & ~(size_t)7;
         size_t stage = (size_t)ts * (4 + nslot) * 8 + (sobol ? (size_t)ts * KK * nw * 4 + (size_t)ts * KK * 32 * 4 : 0);
         size_t mom = (opt.out == OUT_MOMENTS) ? (size_t)nw * 3 * 8 : 0;
@@ -763,7 +770,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         const size_t with4 = smem_for(L.block);
         nstage = 2;
         const size_t with2 = smem_for(L.block);
-        bool use4 = u.T() - 1 > 2 * tt && with4 <= 100 * 1024 && (with4 - with2) * 2 <= with4;
+        bool use4 = u.T() - 1 > 2 * tt && with4 <= 112 * 1024 && (with4 - with2) * 2 <= with4;   // two CTAs per SM still fit
         if (const char* g = std::getenv("SDE_B200_NSTAGE")) use4 = std::atoi(g) == 4 && with4 <= 200 * 1024;   // tuning
         nstage = use4 ? 4 : 2;
     }
@@ -835,7 +842,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         s << "#define SDE_RES_GRP 4\n";                      // steps per unrolled group: one sector store per lane and process
     }
     s << "#define SDE_TT " << L.tt << "\n#define SDE_CH " << L.ch << "\n#define SDE_UNR " << L.unr << "\n#define SDE_NSLOT " << nslot << "\n#define SDE_DIRECT " << (L.direct ? 1 : 0) << "\n";
-    if (L.tma) s << "#define SDE_TMA 1\n";
+    if (L.tma) s << "#define SDE_TMA " << (L.tma2 ? 2 : 1) << "\n";
     if (!L.wide && !L.resident && L.nstage == 4) s << "#define SDE_NSTAGE 4\n";
     s << "#include \"sde_expr_helpers.cuh\"\n#include \"sde_device_icdf.cuh\"\n";
     s << "__device__ __forceinline__ constexpr bool sde_factor_is_wiener(int k) { return ";

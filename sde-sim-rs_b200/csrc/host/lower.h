@@ -29,7 +29,8 @@ struct LowerOptions {
     int min_blocks = 0;      // 0 = auto: CTAs per SM promised to the compiler (__launch_bounds__)
     int direct = -1;         // NTP paths: -1 = auto, 0 = shared-memory transpose, 1 = direct sector stores (tiled kernel),
                              // 2 = persistent-warp kernel with resident tables (sde_sim_resident.cuh),
-                             // 3 = per-lane bulk copies shared -> global (cp.async.bulk; tiled kernel, f64, P even)
+                             // 3 = per-lane bulk copies shared -> global (cp.async.bulk; tiled kernel, f64, P even),
+                             // 4 = per-warp 2-D tensor-map stores (cp.async.bulk.tensor; tiled kernel, f64, P = 2 or 4)
     int wide_mma = -1;       // wide linear models, terminal / moments: -1 = auto, 0 = time-tiled kernel, 1 = require the
                              // FP64 tensor-core kernel (sde_sim_wide.cuh)
 };
@@ -44,6 +45,7 @@ struct Lowered {
     size_t smem_bytes = 0;   // dynamic shared memory of sde_sim_kernel
     bool direct = false;     // NTP full paths leave as 256-bit sector stores from registers (lane stride 4 mapping)
     int nstage = 2;          // time-tiled kernel: stage buffers (2: __syncthreads per tile; 4: mbarrier hand-over, SDE_NSTAGE)
+    bool tma2 = false;       // ... as one 2-D tensor-map store per warp and box (SDE_TMA == 2): the launch takes a CUtensorMap
     bool tma = false;        // NTP full paths leave as per-lane bulk copies from a shared-memory staging row (16-byte aligned buffer)
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory

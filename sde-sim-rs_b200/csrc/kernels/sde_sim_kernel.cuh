@@ -76,6 +76,14 @@
 #ifndef SDE_TMA
 #define SDE_TMA 0
 #endif
+// SDE_TMA == 2: one 2-D tensor-map store per warp and box of SDE_TBOX_STEPS steps (P = 2 or 4: a box row — one path's
+// SDE_TBOX_STEPS x P values — is 128 bytes).  The 32 lanes of a warp own 32 consecutive paths; each writes its row of the box
+// into shared memory with 128-bit stores in the 128-byte swizzle pattern of the tensor map (16-byte chunk c of row r at
+// chunk c ^ (r & 7): conflict free), lane 0 issues cp.async.bulk.tensor.2d shared -> global.  The copy engine writes every
+// row as one 128-byte piece and clips rows / columns outside [N] x [T P] (pad lanes, ragged ends), and none of the store
+// bytes crosses the load/store data pipe as scattered sectors.  Two boxes per warp, ping-pong.
+#define SDE_TBOX_STEPS (16 / SDE_P)
+struct alignas(64) SdeTensorMap { unsigned long long v[16]; };
 #ifndef SDE_ST256
 #define SDE_ST256 1   /* 256-bit st.global.v4.f64 (PTX ISA 8.8 / CUDA 12.9 ptxas) */
 #endif
@@ -92,8 +100,13 @@
 
 // shared-memory carve-up (bytes); mirrored by the host in lower.cpp
 //   icdf tables | output staging tile | 2 x { step records | Sobol CTA/warp part | Sobol lane part } | moment scratch
+#if SDE_TMA == 2
+#define SDE_SMEM_ICDF_BYTES (((SDE_ICDF == 1 && SDE_RNG != 4) ? ((SDE_ICDF_TABLE_DOUBLES * 8 + 1023) & ~1023) : 0))   /* boxes start 1 KB aligned */
+#define SDE_SMEM_TILE_BYTES (SDE_NW * 2 * 4096)
+#else
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1 && SDE_RNG != 4) ? (SDE_ICDF_TABLE_DOUBLES * 8) : 0)
 #define SDE_SMEM_TILE_BYTES ((SDE_OUT == 0 && !SDE_DIRECT) ? (((SDE_NW * 32 * SDE_TILE_LD * (int)sizeof(sde_real) + 7) & ~7)) : 0)
+#endif
 #define SDE_SMEM_STEP_BYTES (SDE_TS * SDE_STEP_LD * 8)
 #define SDE_SMEM_BW_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * SDE_NW * 4) : 0)
 #define SDE_SMEM_LANE_BYTES (SDE_USES_SOBOL ? (SDE_TS * SDE_KK * 32 * 4) : 0)
@@ -154,8 +167,13 @@ struct SdeTilePrefetch {
 #endif
 };
 
+#if SDE_TMA == 2
+extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm, const __grid_constant__ SdeTensorMap tmap) {
+    extern __shared__ __align__(1024) double4 sde_smem_raw[];
+#else
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
     extern __shared__ double4 sde_smem_raw[];
+#endif
     unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
     double* s_icdf = reinterpret_cast<double*>(smem);
     sde_real* s_tile = reinterpret_cast<sde_real*>(smem + SDE_SMEM_ICDF_BYTES);
@@ -307,6 +325,49 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
     const long long s_warp0 = s_local - lane;
     (void)valid_mask; (void)s_warp0;
+#if SDE_TMA == 2
+    // this warp's two boxes; box_row = this lane's 128-byte row with the lane's swizzle term folded in: chunk c of the row
+    // lives at box_row ^ (c << 4) (+ 4096 for the second box)
+    const unsigned box_warp = (unsigned)__cvta_generic_to_shared(s_tile) + (unsigned)warp * 8192u;
+    const unsigned box_row = box_warp + (unsigned)lane * 128u + ((unsigned)(lane & 7) << 4);
+    int box_open = -1;                                        // box (index = step / SDE_TBOX_STEPS) that holds unsent rows
+    // box_send: all rows of box b are in shared memory -> one tensor store by lane 0 (columns (b STEPS + 1) P .., rows s_warp0 ..)
+    auto box_send = [&](const int b) __attribute__((always_inline)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(&tmap), "r"((b * SDE_TBOX_STEPS + 1) * SDE_P), "r"((int)s_warp0), "r"(box_warp + (unsigned)(b & 1) * 4096u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    };
+    // box_rows: the SDE_P values of `ns` consecutive steps starting at step t go into the lane's row of box t / STEPS
+    auto box_put = [&](const int t, const int ns, const sde_real* vals) __attribute__((always_inline)) {
+        if (s_warp0 < 0) {
+            // the copy engine faults on a box that starts at a negative row (measured): the one warp of a launch that holds
+            // the <= 5 leading pad lanes (Sobol::skip(5), sobol.rs:17) writes its rows itself
+            if (valid) {
+                sde_real* dst = out_r + ((size_t)s_local * T + (size_t)(t + 1)) * SDE_P;
+#pragma unroll
+                for (int q = 0; q < SDE_UNR * SDE_P; ++q) if (q < ns * SDE_P) dst[q] = vals[q];
+            }
+            return;
+        }
+        const int b = t / SDE_TBOX_STEPS, so = t - b * SDE_TBOX_STEPS;
+        if (b != box_open) {
+            // a new box: the store that last read this buffer (box b - 2) must be done with it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            box_open = b;
+        }
+        const unsigned base = (box_row + (unsigned)(b & 1) * 4096u) ^ ((unsigned)(so * SDE_P / 2) << 4);
+#pragma unroll
+        for (int q = 0; q < SDE_UNR * SDE_P / 2; ++q)
+            if (q < ns * SDE_P / 2)
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(base ^ ((unsigned)q << 4)), "d"(vals[2 * q]), "d"(vals[2 * q + 1]) : "memory");
+        if (so + ns == SDE_TBOX_STEPS || t + ns == S) { box_send(b); box_open = -1; }
+    };
+#endif
 #endif
 #elif SDE_OUT == 1
     if (valid) {
@@ -535,6 +596,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) vals[j * SDE_P + p] = row[p];
             }
+#if SDE_TMA == 2
+            box_put(tc, SDE_UNR, vals);
+#else
             // the copy engine may still be reading the previous tile's segment from this row: its read is waited for here,
             // a whole group's draws and updates after it was issued (no-op from the second group of a tile on)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -543,6 +607,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll
                 for (int q = 0; q < SDE_UNR * SDE_P / 2; ++q) dst[q] = make_double2(vals[2 * q], vals[2 * q + 1]);
             }
+#endif
 #else
 #pragma unroll
             for (int j = 0; j < SDE_UNR; ++j) advance(tc + j, zu[j], u0[j]);
@@ -559,6 +624,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             if (valid) {
 #pragma unroll
                 for (int p = 0; p < SDE_P; ++p) my_row[(size_t)(t + 1) * SDE_P + p] = row[p];
+            }
+#elif SDE_OUT == 0 && SDE_TMA == 2
+            {
+                sde_real one[SDE_UNR * SDE_P];
+#pragma unroll
+                for (int p = 0; p < SDE_UNR * SDE_P; ++p) one[p] = p < SDE_P ? row[p] : (sde_real)0;
+                box_put(t, 1, one);
             }
 #elif SDE_OUT == 0 && SDE_TMA
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -639,7 +711,9 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         if (more) commit(t0_next, pf, buf ^ 1);               // the other buffer was last read in tile k-1 (barrier below)
 #endif
 
-#if SDE_OUT == 0 && SDE_TMA
+#if SDE_OUT == 0 && SDE_TMA == 2
+        // (boxes leave as they fill: nothing to do at the tile boundary)
+#elif SDE_OUT == 0 && SDE_TMA
         // hand this lane's [t0+1, t_end] x P segment (contiguous in HBM, 16-byte aligned: P is even) to the copy engine
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the lane's own generic-proxy writes -> async proxy
         if (valid) {

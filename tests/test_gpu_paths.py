@@ -239,12 +239,16 @@ def test_persistent_kernel_many_items_per_warp_matches_tiled(scramble, mode):
 
 @pytest.mark.parametrize("rng_method,scramble,scheme,steps,N", [("sobol", "xor", "runge-kutta", 1000, 600), ("pseudo", "cp_shift_per_path", "euler", 37, 300),
                                                             ("sobol", "cp_shift_per_path", "euler", 50, 257)])
-def test_bulk_copy_store_path_is_bit_identical(rng_method, scramble, scheme, steps, N):
-    # ntp_direct=4: rows staged per lane in shared memory and written by cp.async.bulk (P even); same values as the default path
+@pytest.mark.parametrize("mode", [4, 5])
+def test_bulk_copy_store_path_is_bit_identical(rng_method, scramble, scheme, steps, N, mode):
+    # ntp_direct=4: rows staged per lane in shared memory and written by cp.async.bulk (P even); ntp_direct=5: one 2-D
+    # tensor-map store per warp and 128-byte box row (P = 2 or 4); same values as the default path
+    if mode == 5 and rng_method != "sobol":
+        pytest.skip("tensor-map stores ride on 4-step groups (K <= 2, no ChaCha block alignment)")
     times, init = grid(1000, steps), {"S": 100.0, "v": 0.04}
     kw = dict(scramble=scramble, seed=9, scenario_offset=3)
-    a = S.Plan(S.Universe(HESTON_EQ, times), scheme, rng_method, scramble=scramble, ntp_direct=4)
-    assert "#define SDE_TMA 1" in a.source
+    a = S.Plan(S.Universe(HESTON_EQ, times), scheme, rng_method, scramble=scramble, ntp_direct=mode)
+    assert f"#define SDE_TMA {mode - 3}" in a.source
     got = a.run(init, N, seed=9, scenario_offset=3).cpu().numpy()
     ref = S.simulate(HESTON_EQ, times, N, init, rng_method, scheme, **kw).to_numpy()
     assert np.array_equal(got, ref)

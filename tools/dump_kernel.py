@@ -39,7 +39,7 @@ def main():
     o = S._make_options(device=0, seed=0, scenario_offset=0, output=kw.get("output", "paths"), layout=kw.get("layout", "NTP"),
                         scramble=kw.get("scramble", "cp_shift_per_path"), icdf=kw.get("icdf", "reference"),
                         arithmetic=kw.get("arithmetic", "strict"), rk_variant="reference",
-                        tile_steps=int(extra.get("tt", 0)), block_threads=int(extra.get("block", 0)), generator=kw.get("generator", "chacha8"))
+                        tile_steps=int(extra.get("tt", 0)), block_threads=int(extra.get("block", 0)), ntp_direct=int(extra.get("direct", 0)), generator=kw.get("generator", "chacha8"))
     src = C.c_void_p()
     _ffi.check(_ffi.lib().sde_lower_only(u._h, scheme.encode(), rng.encode(), C.byref(o), 0, C.byref(src), None))
     text = C.string_at(src).decode()

@@ -770,7 +770,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         const size_t with4 = smem_for(L.block);
         nstage = 2;
         const size_t with2 = smem_for(L.block);
-        bool use4 = u.T() - 1 > 2 * tt && with4 <= 112 * 1024 && (with4 - with2) * 2 <= with4;   // two CTAs per SM still fit
+        // (not for the ChaCha-driven modes: their step loop is several thousand instructions, and warps that drift apart
+        //  stop sharing the instruction cache — C5 on the reference's ChaCha8 stream 382 -> 418 ms with four buffers)
+        bool use4 = !chacha && u.T() - 1 > 2 * tt && with4 <= 112 * 1024 && (with4 - with2) * 2 <= with4;   // two CTAs per SM still fit
         if (const char* g = std::getenv("SDE_B200_NSTAGE")) use4 = std::atoi(g) == 4 && with4 <= 200 * 1024;   // tuning
         nstage = use4 ? 4 : 2;
     }

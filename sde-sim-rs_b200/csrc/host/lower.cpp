@@ -771,8 +771,9 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
         nstage = 2;
         const size_t with2 = smem_for(L.block);
         // (not for the ChaCha-driven modes: their step loop is several thousand instructions, and warps that drift apart
-        //  stop sharing the instruction cache — C5 on the reference's ChaCha8 stream 382 -> 418 ms with four buffers)
-        bool use4 = !chacha && u.T() - 1 > 2 * tt && with4 <= 112 * 1024 && (with4 - with2) * 2 <= with4;   // two CTAs per SM still fit
+        //  stop sharing the instruction cache — C5 on the reference's ChaCha8 stream 382 -> 418 ms with four buffers;
+        //  for the same reason only small models, K <= 2: the measured cases)
+        bool use4 = !chacha && K <= 2 && u.T() - 1 > 2 * tt && with4 <= 112 * 1024 && (with4 - with2) * 2 <= with4;   // two CTAs per SM still fit
         if (const char* g = std::getenv("SDE_B200_NSTAGE")) use4 = std::atoi(g) == 4 && with4 <= 200 * 1024;   // tuning
         nstage = use4 ? 4 : 2;
     }

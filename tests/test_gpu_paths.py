@@ -333,6 +333,43 @@ def test_full_size_c2_properties():
     torch.cuda.empty_cache()
 
 
+def test_full_size_c3_properties(oracle):
+    # C3 at BASELINE size (Heston, Runge-Kutta, 2^22 paths x 1000 steps, P = 2: 67 GB): the oracle on the first and last paths
+    # of the buffer, and size-independent properties for the rest
+    N, D = 1 << 22, 1000
+    init = {"S": 100.0, "v": 0.04}
+    times = grid(D)
+    plan = S.Plan(S.Universe(HESTON_EQ, times), "runge-kutta", "sobol", scramble="xor", icdf="fast", arithmetic="fast")
+    out = plan.run(init, N, seed=42)
+    assert out.shape == (N, D + 1, 2)
+    assert bool((out[:, 0, 0] == 100.0).all()) and bool((out[:, 0, 1] == 0.04).all())      # t0 row = initial values
+    assert bool(torch.isfinite(out).all()) and bool((out[:, :, 0] > 0).all())
+    U = oracle.Universe(HESTON_EQ, times)
+    head = oracle.simulate(U, init, 48, "runge-kutta", "sobol", seed=42, scramble="xor")
+    tail = oracle.simulate(U, init, 48, "runge-kutta", "sobol", seed=42, scramble="xor", scenario_offset=N - 48)
+    for got, ref in ((out[:48].cpu().numpy(), head), (out[N - 48:].cpu().numpy(), tail)):
+        scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=(0, 1), keepdims=True) * 1e-3)   # v can sit near zero
+        assert np.max(np.abs(got - ref) / scale) <= 1e-10                      # fast tier: 5e-13 per draw, 1000 steps, sqrt(v) near 0
+    # shard check at full size: paths around the middle recomputed with an offset are bit-identical
+    lo = (1 << 21) - 300
+    part = plan.run(init, 777, seed=42, scenario_offset=lo)
+    assert torch.equal(part, out[lo:lo + 777])
+    # the moments-only plan (another store path and the warp-shuffle / block reduction) sees the same terminal values
+    mom = S.simulate(HESTON_EQ, times, N, init, "sobol", "runge-kutta", seed=42, scramble="xor", icdf="fast", arithmetic="fast",
+                     output="moments").to_numpy()
+    term = out[:, -1, :].double()
+    assert mom[0, 0] == N and mom[1, 0] == N
+    for p in range(2):
+        mean = float(term[:, p].mean())
+        assert abs(mom[p, 1] / mean - 1) < 1e-11
+        assert abs(mom[p, 2] / float(((term[:, p] - mean) ** 2).sum()) - 1) < 1e-8
+    # sanity of the model itself: S drifts at 5 % a year (the reference's stale-cache Runge-Kutta variant is not the
+    # textbook scheme: a few 1e-2 relative is all that is claimed), v stays around its mean-reversion level
+    assert abs(mom[0, 1] / (100.0 * np.exp(0.05)) - 1) < 5e-2 and abs(mom[1, 1] - 0.04) < 1e-2
+    del out
+    torch.cuda.empty_cache()
+
+
 def test_full_size_c5_per_gpu_moments_against_closed_form():
     # C5's per-GPU share (2^30 paths x 365 steps, pseudo-random ChaCha8 streams, moments only): closed-form Euler-GBM moments
     N, D = 1 << 30, 365

@@ -323,8 +323,10 @@ std::vector<char> nvrtc_compile(const std::string& source, const std::string& na
     nvrtcProgram prog;
     nvrtcResult r = n.nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), (int)names.size(), ptrs.data(), names.data());
     if (r != NVRTC_SUCCESS) throw CudaError{std::string("nvrtcCreateProgram: ") + n.nvrtcGetErrorString(r)};
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", st256 ? "-DSDE_ST256=1" : "-DSDE_ST256=0"};
-    r = n.nvrtcCompileProgram(prog, 4, opts);
+    // -default-device: the generic lambda that instantiates the persistent kernel's item loop per step shift has no execution
+    // space annotation of its own (nvcc infers it from the enclosing __global__ function, NVRTC asks for the flag)
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", st256 ? "-DSDE_ST256=1" : "-DSDE_ST256=0", "-default-device"};
+    r = n.nvrtcCompileProgram(prog, 5, opts);
     size_t ls = 0;
     n.nvrtcGetProgramLogSize(prog, &ls);
     std::string lg(ls, '\0');

@@ -101,6 +101,15 @@ __device__ __forceinline__ sde_u32 sde_res_fold(sde_u32 x) {
 #endif
 }
 
+// The item loop is instantiated once per step shift gamma = 0..3 (a CTA only takes items of one class, so the shift is
+// CTA-uniform): the <= 3 head steps, the <= 3 tail steps and the <= 2 recomputed steps of the next row's head then have
+// compile-time trip counts, unroll, and their uniform -> normal chains overlap like those of a group instead of running
+// one latency-exposed step at a time.  SDE_RES_GAMMA_SPECIALISE = 0 keeps one copy with a run-time shift.
+#ifndef SDE_RES_GAMMA_SPECIALISE
+#define SDE_RES_GAMMA_SPECIALISE 1
+#endif
+template <int V> struct sde_int_tag { static constexpr int value = V; };
+
 extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_kernel(const SdeParams prm) {
     extern __shared__ double4 sde_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(sde_smem_raw);
@@ -122,8 +131,8 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     // starts at step gamma writes elements from (gamma + 1) P on — P (s T + gamma + 1) = 0 (mod 4) puts that on a
     // 32-byte boundary (the output base is 32-byte aligned); s = n - first_n = cls - first_n (mod 4) for every lane
     const int cls = (int)(blockIdx.x & 3u);
-    const int gamma = (4 - (int)((((long long)(n_base + (sde_u64)cls) - (long long)first_n) * T + 1) & 3)) & 3;
-    const int off = (4 - ((gamma * SDE_K) & 3)) & 3;          // (gamma K + off) = 0 (mod 4): groups start on a quad
+    const int gamma_rt = (4 - (int)((((long long)(n_base + (sde_u64)cls) - (long long)first_n) * T + 1) & 3)) & 3;
+    const int off = (4 - ((gamma_rt * SDE_K) & 3)) & 3;       // (gamma K + off) = 0 (mod 4): groups start on a quad
 
     // ---- CTA prologue: the tables every path of every item reads
 #if SDE_ICDF == 1
@@ -174,6 +183,13 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     const double t_first = __ldg(prm.times);
     const sde_u64 m_stride = (sde_u64)(gridDim.x >> 2) * SDE_NW;
 
+    auto run_items = [&](auto gamma_tag) __attribute__((always_inline)) {
+#if SDE_RES_GAMMA_SPECIALISE
+    constexpr int gamma = decltype(gamma_tag)::value;         // this CTA's step shift, compile time in this instance
+#else
+    const int gamma = gamma_rt;
+    (void)gamma_tag;
+#endif
 #pragma unroll 1
     for (sde_u64 m = (sde_u64)(blockIdx.x >> 2) * SDE_NW + warp; m < n_blocks; m += m_stride) {
         // item = 32 paths n = n0 + 4 lane of block m
@@ -343,6 +359,22 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         // the first row's head and the last row's tail of a launch go out as scalars.
         double hv[4];
         hv[0] = row[0];
+#if SDE_RES_GAMMA_SPECIALISE
+        {
+            // the g_eff head steps: all draws first (independent chains), then the serial state updates
+            double hz[3][SDE_KK];
+            sde_u0_t hu[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) if (j < g_eff) draw(j, hz[j], hu[j]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < g_eff) {
+                    sde_model_step(row, cache, ct, hz[j], hu[j], s_step + j * SDE_STEP_LD);
+                    hv[j + 1] = row[0];
+                }
+            t = g_eff;
+        }
+#else
 #pragma unroll 1
         for (; t < g_eff; ++t) {
             double zu[SDE_KK];
@@ -351,6 +383,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
             if (t == 0) hv[1] = row[0]; else if (t == 1) hv[2] = row[0]; else hv[3] = row[0];
         }
+#endif
         if (gamma == 3 && g_eff == 3) {
             const int lv = valid ? 1 : 0;
             asm volatile("{ .reg .pred p; setp.ne.s32 p, %5, 0; @p st.global.v4.f64 [%0], {%1, %2, %3, %4}; }"
@@ -442,6 +475,26 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #endif
 #if SDE_FULL_SECTORS
         {
+#if SDE_RES_GAMMA_SPECIALISE
+            constexpr int g_c = gamma < S ? gamma : S;
+            constexpr int t_tail = g_c + ((S - g_c) / SDE_RES_GRP) * SDE_RES_GRP;
+            constexpr int r = S - t_tail;                     // 0..3 tail elements; they start on a sector boundary
+            double tv[3];
+            tv[0] = tv[1] = tv[2] = 0.0;
+            {
+                double tz[3][SDE_KK];
+                sde_u0_t tu[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (j < r) draw(t_tail + j, tz[j], tu[j]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < r) {
+                        sde_model_step(row, cache, ct, tz[j], tu[j], s_step + (t_tail + j) * SDE_STEP_LD);
+                        tv[j] = row[0];
+                    }
+            }
+            t = S;
+#else
             const int r = S - t;                              // 0..3 tail elements; they start on a sector boundary
             const int t_tail = t;
             double tv[3];
@@ -449,11 +502,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
 #pragma unroll 1
             for (; t < S; ++t) {
                 double zu[SDE_KK];
-            sde_u0_t u0;
+                sde_u0_t u0;
                 draw(t, zu, u0);
                 sde_model_step(row, cache, ct, zu, u0, s_step + t * SDE_STEP_LD);
                 if (t == t_tail) tv[0] = row[0]; else if (t == t_tail + 1) tv[1] = row[0]; else tv[2] = row[0];
             }
+#endif
             if (r > 0) {
                 const bool has_next = valid && (sde_u64)(s_local + 1) < prm.n_paths;
                 if (__any_sync(0xffffffffu, has_next)) {
@@ -464,6 +518,27 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                     double row2[SDE_P], cache2[SDE_P];
                     double ct2 = t_first;
                     row2[0] = x0[0]; cache2[0] = x0[0];
+#if SDE_RES_GAMMA_SPECIALISE
+                    {
+                        double nz[2][SDE_KK];
+                        sde_u0_t nu[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (j < 3 - r) {
+                                sde_u32 flip[SDE_KK];
+#pragma unroll
+                                for (int k = 0; k < SDE_K; ++k)   // V_d[b] = nibble-table entry of the single-bit nibble value
+                                    flip[k] = sde_res_fold(__ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k)));
+                                draw_x(j, flip, nz[j], nu[j]);
+                            }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (j < 3 - r) {
+                                sde_model_step(row2, cache2, ct2, nz[j], nu[j], s_step + j * SDE_STEP_LD);
+                                nh[j + 1] = row2[0];
+                            }
+                    }
+#else
 #pragma unroll 1
                     for (int j = 0; j < 3 - r; ++j) {
                         sde_u32 flip[SDE_KK];
@@ -471,11 +546,12 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
                         for (int k = 0; k < SDE_K; ++k)       // V_d[b] = nibble-table entry of the single-bit nibble value
                             flip[k] = sde_res_fold(__ldg(prm.sobol_nib + (size_t)((b >> 2) * 16u + (1u << (b & 3u))) * SDE_NIB_LD + (j * SDE_K + k)));
                         double zu[SDE_KK];
-            sde_u0_t u0;
+                        sde_u0_t u0;
                         draw_x(j, flip, zu, u0);
                         sde_model_step(row2, cache2, ct2, zu, u0, s_step + j * SDE_STEP_LD);
                         if (j == 0) nh[1] = row2[0]; else nh[2] = row2[0];
                     }
+#endif
                     // sector = [tail (r), next head (4 - r)]
                     const double o1 = r >= 2 ? tv[1] : nh[0];
                     const double o2 = r == 3 ? tv[2] : (r == 2 ? nh[0] : nh[1]);
@@ -494,4 +570,15 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         for (; t < S; ++t) single(t);
 #endif
     }
+    };
+#if SDE_RES_GAMMA_SPECIALISE
+    switch (gamma_rt) {
+        case 0: run_items(sde_int_tag<0>{}); break;
+        case 1: run_items(sde_int_tag<1>{}); break;
+        case 2: run_items(sde_int_tag<2>{}); break;
+        default: run_items(sde_int_tag<3>{}); break;
+    }
+#else
+    run_items(sde_int_tag<0>{});
+#endif
 }

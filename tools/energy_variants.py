@@ -25,6 +25,9 @@ CFG = {
 name = sys.argv[1]
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 eqs, D, init, N, scheme, rng, kw = CFG[name]
+for a in sys.argv[3:]:
+    k, v = a.split("=")
+    kw[k] = int(v) if v.lstrip("-").isdigit() else v
 plan = S.Plan(S.Universe(eqs, grid(D)), scheme, rng, **kw)
 out = torch.empty(plan.output_shape(N), dtype=torch.float64, device="cuda")
 plan.run(init, N, seed=42, out=out)
@@ -63,6 +66,6 @@ half = [s for s in samples if s[0] > t0 + 0.5 * (t1 - t0) and s[0] < t1]
 tail = ms[launches // 2:]
 clk = sorted(s[1] for s in half)[len(half) // 2] if half else 0
 pw = sum(s[2] for s in half) / max(1, len(half))
-tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("SDE_B200_D"))
+tag = " ".join([f"{k}={v}" for k, v in os.environ.items() if k.startswith("SDE_B200_")] + sys.argv[3:])
 print(f"{name} [{tag or 'default'}]: first 5 launches {sum(ms[:5]) / 5:.3f} ms; second half {sum(tail) / len(tail):.3f} ms/launch, "
       f"SM {clk} MHz, board {pw:.0f} W, {pw * sum(tail) / len(tail) / 1e3:.2f} J/launch ({len(half)} NVML samples)", flush=True)

@@ -205,7 +205,16 @@ Plan::Plan(const Universe& u, const PlanOptions& opt) : u_(u), opt_(opt) {
             nib.swap(nt);
         }
         d_nib_.upload(nib.data(), nib.size() * 4);
-        d_lane_.upload(lane.data(), lane.size() * 4);
+        if (low_.lane_global) {
+            // sde_sim_resident.cuh with SDE_RES_LANE_GLOBAL reads the table as the CTA prologue would have built it in shared
+            // memory; it depends on the digital-shift masks, i.e. on the seed (ensure_masks); without masks it is final now
+            lane_host_ = lane;
+            const size_t nq = (dims + 6) / 4;
+            d_lane_.alloc(4 * nq * 128 * 4);
+            if (opt_.lower.rng != RNG_SOBOL_XOR) upload_prepared_lane_table(nullptr);
+        } else {
+            d_lane_.upload(lane.data(), lane.size() * 4);
+        }
         if (opt_.lower.rng == RNG_SOBOL_XOR) d_masks_.alloc(dims * 4);
     }
     trace.mark("tables (host build + upload)");
@@ -258,6 +267,22 @@ void Plan::set_initial_values(const std::vector<std::pair<std::string, double>>&
     cu_check(d.cuMemcpyHtoD(d_x0_.ptr(), x0_host_.data(), x0_host_.size() * 8), "cuMemcpyHtoD(x0)");
 }
 
+void Plan::upload_prepared_lane_table(const uint32_t* masks) {
+    const size_t dims = lane_host_.size() / 32, nq = (dims + 6) / 4;
+    std::vector<uint32_t> t(4 * nq * 128, 0u);
+    for (size_t off = 0; off < 4; ++off)
+        for (size_t dd0 = 0; dd0 < dims; ++dd0) {
+            const size_t dd = dd0 + off;
+            const uint32_t m = masks ? masks[dd0] : 0u;
+            for (size_t l = 0; l < 32; ++l) {
+                uint32_t v = lane_host_[dd0 * 32 + l] ^ m;
+                if (low_.res_fold) v ^= (uint32_t)((int32_t)v >> 31) & 0x7fffffffu;     // sign-folded form (SDE_RES_FOLD)
+                t[off * nq * 128 + ((dd >> 2) * 32 + l) * 4 + (dd & 3)] = v;
+            }
+        }
+    cu_check(driver().cuMemcpyHtoD(d_lane_.ptr(), t.data(), t.size() * 4), "cuMemcpyHtoD(prepared lane table)");
+}
+
 void Plan::ensure_masks(uint64_t seed, CUstream stream) {
     if (opt_.lower.rng != RNG_SOBOL_XOR || d_masks_.bytes() == 0) return;
     if (masks_valid_ && masks_seed_ == seed) return;
@@ -269,6 +294,7 @@ void Plan::ensure_masks(uint64_t seed, CUstream stream) {
     const DriverApi& d = driver();
     cu_check(d.cuStreamSynchronize(stream), "cuStreamSynchronize");
     cu_check(d.cuMemcpyHtoD(d_masks_.ptr(), m.data(), m.size() * 4), "cuMemcpyHtoD(masks)");
+    if (low_.lane_global) upload_prepared_lane_table(m.data());
     masks_valid_ = true;
     masks_seed_ = seed;
 }

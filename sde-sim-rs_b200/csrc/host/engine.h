@@ -63,6 +63,8 @@ class Plan {
     CUmodule mod_ = nullptr;
     CUfunction fn_sim_ = nullptr, fn_fin_ = nullptr;
     DeviceBuffer d_times_, d_dts_, d_sqrt_dts_, d_x0_, d_nib_, d_lane_, d_masks_, d_partials_;
+    std::vector<uint32_t> lane_host_;     // persistent kernel with the lane table in global memory: x_d(4 lane), [dims][32]
+    void upload_prepared_lane_table(const uint32_t* masks);   // [4 offsets][quads][32 lanes][4]: mask and sign fold applied
     std::vector<double> x0_host_;
     bool masks_valid_ = false;
     uint64_t masks_seed_ = 0;

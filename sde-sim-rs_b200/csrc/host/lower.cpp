@@ -654,11 +654,12 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     {
         const int S = u.T() - 1;
         bool wide = false;                                    // 1024-entry log table (128 KB): XOR digital shift only
+        bool lane_global = false;                             // lane table in global memory (SDE_RES_LANE_GLOBAL)
         auto resident_smem = [&](int block, int nslot_) {     // mirrors the SDE_SMEM_* macros of sde_sim_resident.cuh
             const size_t sk = (size_t)S * K;
             size_t icdf = (opt.icdf == 1) ? (wide ? (size_t)1024 * 2 * 8 * 8 : (size_t)(128 * 2 * 8 + 64) * 8) : 0;
             const size_t nq = (sk + 3 + 3) / 4;               // SDE_NQ: quads of 4 dimensions (+ room for the per-CTA offset)
-            return icdf + (size_t)S * (4 + nslot_) * 8 + nq * 512 + (size_t)(block / 32) * nq * 16;
+            return icdf + (size_t)S * (4 + nslot_) * 8 + (lane_global ? 0 : nq * 512) + (size_t)(block / 32) * nq * 16;
         };
         const bool eligible = sector_stores_ok && (opt.rng == RNG_SOBOL_XOR || opt.rng == RNG_SOBOL_RAW) && K >= 1;
         if (eligible && opt.direct != 1 && opt.direct != 3 && opt.direct != 4) {
@@ -668,11 +669,24 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
             int block = opt.block > 0 ? opt.block : 768;
             block = std::max(32, std::min(1024, (block / 32) * 32));   // warps are autonomous: any whole number of warps
             while (block > 32 && resident_smem(block, nslot) > 200 * 1024) block = std::max(32, (block / 64) * 32);
+            if (resident_smem(block, nslot) > 200 * 1024 && opt.direct == 2) {
+                // the tables of the whole time grid do not fit (C3: 2000 dimensions) and the persistent kernel was asked for
+                // (ntp_direct = 3): keep the lane table in global memory, prepared by the host; the per-warp Sobol part (16
+                // bytes per quad and warp) decides how many warps fit.  Not selected automatically: on C3 it runs at
+                // 24.3 ms against 24.0-24.1 ms for the time-tiled kernel with the four-buffer hand-over (same box)
+                lane_global = true;
+                block = opt.block > 0 ? std::max(32, std::min(1024, (opt.block / 32) * 32)) : 768;
+                while (block > 128 && resident_smem(block, nslot) > 200 * 1024) block -= 128;
+            }
             if (resident_smem(block, nslot) <= 200 * 1024) {
                 wide = opt.icdf == 1 && opt.rng == RNG_SOBOL_XOR && !std::getenv("SDE_B200_NO_WIDE_TABLE");
                 if (wide && resident_smem(block, nslot) > 220 * 1024) wide = false;
                 L.icdf_wide = wide;
                 L.resident = true;
+                L.lane_global = lane_global;
+                // mirrors SDE_RES_FOLD of sde_sim_resident.cuh: the host prepares the global lane table in the same form
+                L.res_fold = opt.rng == RNG_SOBOL_XOR && opt.icdf == 1 && opt.scheme != SCHEME_RK &&
+                             std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; });
                 L.direct = true;
                 L.block = block;
                 L.smem_bytes = resident_smem(block, nslot);
@@ -837,6 +851,7 @@ Lowered lower_model(const Universe& u, const LowerOptions& opt_in) {
     if (L.resident) {
         s << "#define SDE_S " << (u.T() - 1) << "\n";
         if (L.icdf_wide) s << "#define SDE_ICDF_WIDE 1\n";
+        if (L.lane_global) s << "#define SDE_RES_LANE_GLOBAL 1\n";
         if (K > 0 && std::all_of(u.factor_is_wiener.begin(), u.factor_is_wiener.end(), [](bool b) { return b; })) s << "#define SDE_ALL_WIENER 1\n";
         if (std::getenv("SDE_B200_DEBUG_NOCOMPUTE")) s << "#define SDE_DEBUG_NOCOMPUTE 1\n";                                              // profiling aid
         if (std::getenv("SDE_B200_DEBUG_NOSCALAR")) s << "#define SDE_DEBUG_NOSCALAR 1\n";                                                // profiling aid

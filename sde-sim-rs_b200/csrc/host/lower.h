@@ -48,6 +48,8 @@ struct Lowered {
     bool tma2 = false;       // ... as one 2-D tensor-map store per warp and box (SDE_TMA == 2): the launch takes a CUtensorMap
     bool tma = false;        // NTP full paths leave as per-lane bulk copies from a shared-memory staging row (16-byte aligned buffer)
     bool icdf_wide = false;  // persistent kernel: 1024-entry inverse-normal log table (128 KB of shared memory)
+    bool lane_global = false; // persistent kernel: lane table prepared by the host in global memory (SDE_RES_LANE_GLOBAL)
+    bool res_fold = false;   // persistent kernel: the tables hold sign-folded words (mirrors SDE_RES_FOLD)
     bool resident = false;   // persistent-warp kernel (sde_sim_resident.cuh): grid = SMs x min_blocks, whole time grid in shared memory
     bool wide = false;       // tensor-core kernel for wide linear models (sde_sim_wide.cuh): persistent warps, 8 wide_mt paths per warp
     int wide_mt = 0;         // row tiles (of 8 paths) per warp

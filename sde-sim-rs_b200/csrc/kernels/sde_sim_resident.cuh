@@ -87,7 +87,15 @@
 #define SDE_ICDF_WIDE 0                         /* 1: 1024-entry log table (128 KB), set by the lowering when it fits */
 #endif
 #define SDE_SMEM_ICDF_BYTES ((SDE_ICDF == 1) ? ((SDE_ICDF_WIDE ? SDE_ICDF_WIDE_DOUBLES : SDE_ICDF_TABLE_DOUBLES) * 8) : 0)
-#define SDE_SMEM_LANE_BYTES (SDE_NQ * 32 * 16)
+// SDE_RES_LANE_GLOBAL: the lane table stays in global memory (time grids whose table does not fit in shared memory: C3 has
+// 2000 dimensions = 256 KB).  The host prepares it per seed in the layout the CTA prologue would build — digital shift
+// folded in, sign-folded where the plan folds, [off][quad][lane][4] for every quad offset 0..3 — and prm.sobol_lane points at
+// it; a group's words are then one 128-bit read-only global load per quad (L1 / L2 resident: every warp of the GPU reads the
+// same 256 KB) issued a whole group ahead by the software pipeline, instead of a shared-memory load.
+#ifndef SDE_RES_LANE_GLOBAL
+#define SDE_RES_LANE_GLOBAL 0
+#endif
+#define SDE_SMEM_LANE_BYTES (SDE_RES_LANE_GLOBAL ? 0 : (SDE_NQ * 32 * 16))
 #define SDE_SMEM_STEP_BYTES (SDE_S * SDE_STEP_LD * 8)
 #define SDE_SMEM_BW_BYTES (SDE_NW * SDE_BW_LD * 4)
 #define SDE_SMEM_BYTES (SDE_SMEM_ICDF_BYTES + SDE_SMEM_STEP_BYTES + SDE_SMEM_LANE_BYTES + SDE_SMEM_BW_BYTES)
@@ -142,6 +150,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     sde_icdf_table_load(s_icdf, tid, SDE_BLOCK, SDE_RNG == 2 ? SDE_ICDF_Y_OFFSET_K32 : 0.0);
 #endif
 #endif
+#if !SDE_RES_LANE_GLOBAL
     for (int e = tid; e < SDE_SK * 32; e += SDE_BLOCK) {
         const int d = e >> 5, l = e & 31;
         sde_u32 v = __ldg(prm.sobol_lane + e);
@@ -151,6 +160,7 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
         const int dd = d + off;
         s_lane[(((dd >> 2) << 5) + l) * 4 + (dd & 3)] = sde_res_fold(v);
     }
+#endif
     for (int e = tid; e < S; e += SDE_BLOCK) {
         const double t_cur = __ldg(prm.times + e), t_next = __ldg(prm.times + e + 1);
         const double dt = __ldg(prm.dts + e), sq = __ldg(prm.sqrt_dts + e);
@@ -168,13 +178,23 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
     sde_u32* const my_bw = s_bw + warp * SDE_BW_LD;
     // shared-window byte addresses of the words of "step 0" in this lane's column of the lane table / in this warp's part
     // (explicit ld.shared.v4.u32 in draw_group): the quad of step tg is 128 K tg / 4 K tg bytes further on
+#if SDE_RES_LANE_GLOBAL
+    // this class's copy of the prepared table (quad offset `off` already applied by the host), this lane's column
+    const sde_u32* const g_col = prm.sobol_lane + (size_t)off * (SDE_NQ * 128) + lane * 4;
+    const sde_u32* const g_lane = g_col + off * 32;           // words of "step 0": a group's first quad is 128 K tg bytes further on
+#else
     const sde_u32 lane_t0 = (sde_u32)__cvta_generic_to_shared(s_lane + lane * 4) + (sde_u32)off * 128u;
+#endif
     const sde_u32 bw_t0 = (sde_u32)__cvta_generic_to_shared(my_bw) + (sde_u32)off * 4u;
 #if SDE_ICDF == 1
     const sde_u32 tab_lane = (sde_u32)__cvta_generic_to_shared(s_icdf + 2 * (lane & (SDE_ICDF_TABLE_REPL - 1)));
 #endif
     // word of dimension d: lane part / warp part (scalar accesses: row heads and tails)
+#if SDE_RES_LANE_GLOBAL
+    auto lane_word = [&](const int d) __attribute__((always_inline)) { const int dd = d + off; return __ldg(g_col + ((dd >> 2) << 7) + (dd & 3)); };
+#else
     auto lane_word = [&](const int d) __attribute__((always_inline)) { const int dd = d + off; return s_lane[(((dd >> 2) << 5) + lane) * 4 + (dd & 3)]; };
+#endif
     auto bw_word = [&](const int d) __attribute__((always_inline)) { return my_bw[d + off]; };
 
     double x0[SDE_P];
@@ -313,14 +333,25 @@ extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_MIN_BLOCKS) sde_sim_
             for (int j = 0; j < SDE_RES_GRP; ++j) { u0[j] = (sde_u0_t)0; zu[j][0] = (double)(tg + j) * 1e-4; }
             return;
 #endif
-            sde_u32 la, ba;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(la) : "r"(tg), "n"(128 * SDE_K), "r"(lane_t0));
+            sde_u32 ba;
             asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ba) : "r"(tg), "n"(4 * SDE_K), "r"(bw_t0));
             sde_u32 lw[4 * SDE_QPG], bw[4 * SDE_QPG];
+#if SDE_RES_LANE_GLOBAL
+            const sde_u32* gl;                                // the group's first quad in this lane's column (bytes: 128 K tg further on)
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(gl) : "r"(tg), "n"(128 * SDE_K), "l"(g_lane));
+#else
+            sde_u32 la;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(la) : "r"(tg), "n"(128 * SDE_K), "r"(lane_t0));
+#endif
 #pragma unroll
             for (int i = 0; i < SDE_QPG; ++i) {
+#if SDE_RES_LANE_GLOBAL
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lw[4 * i]), "=r"(lw[4 * i + 1]), "=r"(lw[4 * i + 2]), "=r"(lw[4 * i + 3]) : "l"(gl + i * 128) : "memory");
+#else
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(lw[4 * i]), "=r"(lw[4 * i + 1]), "=r"(lw[4 * i + 2]), "=r"(lw[4 * i + 3]) : "r"(la + i * 512u) : "memory");
+#endif
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(bw[4 * i]), "=r"(bw[4 * i + 1]), "=r"(bw[4 * i + 2]), "=r"(bw[4 * i + 3]) : "r"(ba + i * 16u) : "memory");
             }

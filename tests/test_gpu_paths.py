@@ -256,6 +256,22 @@ def test_bulk_copy_store_path_is_bit_identical(rng_method, scramble, scheme, ste
         S.Plan(S.Universe(GBM_EQ, times), "euler", "pseudo", ntp_direct=4)
 
 
+@pytest.mark.parametrize("scheme,scramble,kw", [("runge-kutta", "xor", dict(icdf="fast", arithmetic="fast")), ("euler", "xor", dict(icdf="fast", arithmetic="fast")),
+                                                 ("runge-kutta", "none", dict())])
+def test_persistent_kernel_with_global_lane_table_is_bit_identical(scheme, scramble, kw):
+    # ntp_direct=3 on a time grid whose lane table does not fit in shared memory (2 x 1000 dimensions): the table is prepared
+    # by the host in global memory (per seed); same values as the time-tiled kernel the lowering picks on its own
+    times, init, N = grid(1000), {"S": 100.0, "v": 0.04}, 700
+    forced = S.Plan(S.Universe(HESTON_EQ, times), scheme, "sobol", scramble=scramble, ntp_direct=3, **kw)
+    assert "#define SDE_RES_LANE_GLOBAL 1" in forced.source
+    auto = S.Plan(S.Universe(HESTON_EQ, times), scheme, "sobol", scramble=scramble, **kw)
+    assert "sde_sim_kernel.cuh" in auto.source
+    for seed, off in ((9, 3), (10, 251)):                  # a second seed: the prepared table follows the masks
+        a = forced.run(init, N, seed=seed, scenario_offset=off)
+        b = auto.run(init, N, seed=seed, scenario_offset=off)
+        assert torch.equal(a, b)
+
+
 def test_direct_store_needs_aligned_output():
     plan = S.Plan(S.Universe(GBM_EQ, grid(252, 8)), "euler", "sobol", scramble="xor")
     buf = torch.empty(100 * 9 + 1, dtype=torch.float64, device="cuda")

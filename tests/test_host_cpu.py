@@ -221,6 +221,7 @@ def test_lowering_cache_rule_euler_vs_rk():
     ("C3-fast-raw", HESTON_EQ, grid(250), "runge-kutta", "sobol", {"scramble": "none", "icdf": "fast", "arithmetic": "fast"}),
     ("C3-fast-philox", HESTON_EQ, grid(1000), "runge-kutta", "pseudo", {"output": "terminal", "icdf": "fast", "arithmetic": "fast", "generator": "philox"}),
     ("C3-fast-f32", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor", "icdf": "single", "arithmetic": "fast", "dtype": "f32"}),
+    ("C3-fast-resident-global-lane-table", HESTON_EQ, grid(1000), "runge-kutta", "sobol", {"scramble": "xor", "icdf": "fast", "arithmetic": "fast", "ntp_direct": 3}),
     ("C3-fast-cp", HESTON_EQ, grid(100), "runge-kutta", "sobol", {"icdf": "fast", "arithmetic": "fast"}),
     ("C5", GBM_EQ, grid(365), "euler", "pseudo", {"output": "moments", "icdf": "fast"}),
     ("jump", ["dX0 = ( 2.0 * (0.5 - X0) ) * dt + ( 0.1 ) * dW1",
@@ -236,6 +237,10 @@ def test_lowering_cache_rule_euler_vs_rk():
 def test_configs_lower_and_compile_for_sm100a(name, eqs, times, scheme, rng, kw):
     text, nbytes = _lower(eqs, times, scheme, rng, compile=1, **kw)     # NVRTC --gpu-architecture=sm_100a, no GPU needed
     assert ('#include "sde_sim_kernel.cuh"' in text or '#include "sde_sim_resident.cuh"' in text) and nbytes > 10_000
+    if name == "C3-fast-resident-global-lane-table":                    # 2000 dimensions: the lane table stays in global memory
+        assert '#include "sde_sim_resident.cuh"' in text and "#define SDE_RES_LANE_GLOBAL 1" in text and "#define SDE_BLOCK 512" in text
+    if name == "C3-fast-tiled":
+        assert '#include "sde_sim_kernel.cuh"' in text and "#define SDE_NSTAGE 4" in text
     if name == "C2-xor-fast":                                           # Sobol full paths with resident tables: persistent warps
         assert '#include "sde_sim_resident.cuh"' in text and "#define SDE_S 252" in text
 

@@ -118,3 +118,61 @@ def test_generated_source_shows_the_grouping():
     assert step.count("sde_f_sqrt_max0_fast(c[1])") == 2                 # one per process block (Euler)
     assert "fma(SDE_SLOT_2, zu[1], (SDE_SLOT_1 * zu[0]))" in step        # 0.2 sqrt(dt) z1 - 0.1 sqrt(dt) z2: one group
     assert "n0 = fma(c[0], fma(" in step                                  # X * (a + q * w) added onto row[0]
+
+
+def _random_model(rng):
+    """A random 2-process model whose coefficients are products / sums of bounded factors, so that paths stay finite whatever
+    the draw: the shapes the factoring pass has to get right (shared and unshared factors, literals on either side, negations,
+    division by literals, sums inside factors, repeated increments)."""
+    names = ["X", "Y"]
+
+    def factor():
+        v = names[rng.integers(2)]
+        w = names[rng.integers(2)]
+        c = round(float(rng.uniform(0.2, 1.5)), 3)
+        return [f"sin({v})", f"cos({c} * {w})", f"tanh({v} - {w})", f"max({v}, 0.0)^0.5", f"({c} - tanh({v}))", f"abs(sin({v} + t))",
+                f"(sin({v})^2)", f"(1.0 + cos(t))", f"tanh({v})"][rng.integers(9)]
+
+    def coeff():
+        k = round(float(rng.uniform(-0.6, 0.6)), 3)
+        parts = [factor() for _ in range(rng.integers(0, 4))]
+        style = rng.integers(5)
+        if not parts:
+            return f"{k}"
+        body = " * ".join(parts)
+        if style == 0:
+            return f"{k} * {body}"
+        if style == 1:
+            return f"{body} * {k}"
+        if style == 2:
+            return f"-({body}) * {abs(k)}"
+        if style == 3:
+            return f"{body} / {round(1.0 / max(abs(k), 0.05), 3)}"
+        return f"{parts[0]} * {k} * " + " * ".join(parts[1:] + ["1.0"])
+
+    eqs = []
+    for n in names:
+        terms = [f"( {coeff()} ) * dt"]
+        for _ in range(rng.integers(1, 4)):
+            terms.append(f"( {coeff()} ) * dW{rng.integers(1, 3)}")
+        if rng.integers(3) == 0:
+            terms.append(f"( {coeff()} ) * dt")
+        eqs.append(f"d{n} = " + " + ".join(terms))
+    return eqs
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("scheme", ["euler", "runge-kutta"])
+def test_factored_lowering_random_models(oracle, seed, scheme):
+    rng = np.random.default_rng(1000 + seed)
+    eqs = _random_model(rng)
+    times, init, N = grid(100, 40), {"X": 0.7, "Y": 0.4}, 128
+    U = oracle.Universe(eqs, times)
+    K = U.K
+    if K == 0:
+        pytest.skip("no stochastic factor drawn")
+    ref, strict, fast = _both(oracle, eqs, times, init, N, [True] * K, scheme, seed=seed)
+    assert np.isfinite(ref).all(), eqs
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=(0, 1), keepdims=True) * 1e-3)
+    assert np.max(np.abs(strict - ref) / scale) <= 1e-12, eqs
+    assert np.max(np.abs(fast - ref) / scale) <= 1e-11, (eqs, np.max(np.abs(fast - ref) / scale))
